@@ -1,0 +1,132 @@
+// fp32 GEMM with fused epilogues:  C = R + gate * ( act(A . W^T + bias) * alpha )
+//
+// Serves every dense projection of the hot path at fp32 accuracy (bit-exact-greedy parity needs fp32-grade sums;
+// the reference's CPU path is fp32): encoder_embedder, conv1/conv2 (as im2col-free GEMMs over a padded
+// token-major buffer, see RowMap), Whisper q/k/v/out/fc1/fc2 in encoder + prefill, DiT qkv/out/fc1/fc2/adaLN.
+//   A: [M, K] via RowMap (K contiguous), W: [N, K] row-major (torch Linear layout), C/R: [M, N] via RowMap.
+// Tile 128x128x16, 256 threads, 8x8 micro-tile, double-buffered shared memory with register prefetch.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mb200 {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+
+__global__ void __launch_bounds__(256, 2) gemm_f32_kernel(GemmParams p) {
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long m0 = (long long)blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+
+    // global->smem loader coordinates: two rows per operand per thread, one float4 along K each
+    const int lrow = tid >> 2;           // 0..63
+    const int lk = (tid & 3) * 4;        // 0,4,8,12
+    const float* a_ptr[2];
+    const float* w_ptr[2];
+    bool a_ok[2], w_ok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        long long m = m0 + lrow + h * 64;
+        a_ok[h] = m < p.M;
+        a_ptr[h] = a_ok[h] ? p.A.row(m) : p.A.ptr;
+        int n = n0 + lrow + h * 64;
+        w_ok[h] = n < p.N;
+        w_ptr[h] = p.W + (long long)(w_ok[h] ? n : 0) * p.ldw;
+    }
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float4 ra[2], rw[2];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int k = k0 + lk;
+            ra[h] = (a_ok[h] && k < p.K) ? __ldg(reinterpret_cast<const float4*>(a_ptr[h] + k)) : make_float4(0, 0, 0, 0);
+            rw[h] = (w_ok[h] && k < p.K) ? __ldg(reinterpret_cast<const float4*>(w_ptr[h] + k)) : make_float4(0, 0, 0, 0);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int r = lrow + h * 64;
+            As[buf][lk + 0][r] = ra[h].x; As[buf][lk + 1][r] = ra[h].y; As[buf][lk + 2][r] = ra[h].z; As[buf][lk + 3][r] = ra[h].w;
+            Bs[buf][lk + 0][r] = rw[h].x; Bs[buf][lk + 1][r] = rw[h].y; Bs[buf][lk + 2][r] = rw[h].z; Bs[buf][lk + 3][r] = rw[h].w;
+        }
+    };
+
+    const int nk = (p.K + BK - 1) / BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue --------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= p.M) continue;
+        float* crow = p.C.row(m);
+        const float* rrow = p.R.ptr ? p.R.row(m) : nullptr;
+        const float* grow = p.gate ? p.gate + (m / p.gate_rpb) * p.gate_ld : nullptr;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            int n = n0 + jh * 64 + tx * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int nn = n + j;
+                if (nn >= p.N) continue;
+                float v = acc[i][jh * 4 + j];
+                if (p.bias) v += __ldg(p.bias + nn);
+                v = apply_act(v, p.act) * p.alpha;
+                if (grow) v *= __ldg(grow + nn);
+                if (rrow) v += rrow[nn];
+                crow[nn] = v;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+    MB_REQUIRE(p.K % 4 == 0, "GEMM K must be a multiple of 4 (float4 loads)");
+    MB_REQUIRE(p.A.ld % 4 == 0 && p.ldw % 4 == 0, "GEMM operand row strides must be multiples of 4 floats");
+    MB_REQUIRE((reinterpret_cast<uintptr_t>(p.A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0,
+               "GEMM operands must be 16-byte aligned");
+    if (p.M <= 0 || p.N <= 0) return 0;
+    dim3 grid((p.N + BN - 1) / BN, (unsigned)((p.M + BM - 1) / BM));
+    gemm_f32_kernel<<<grid, 256, 0, stream>>>(p);
+    MB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace mb200

@@ -1,0 +1,170 @@
+// Internal kernel-launch API of the engine (C++ side; the public C ABI is include/mapperatorinator_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace mb200 {
+
+// ---- gemm.cu ---------------------------------------------------------------------------------------------------------
+struct GemmParams {
+    RowMap A;               // [M, K]
+    const float* W;         // [N, K] row-major
+    long long ldw;
+    RowMap C;               // [M, N]
+    const float* bias;      // [N] or null
+    int act;                // Act
+    float alpha;            // applied after the activation
+    const float* gate;      // per-sample channel gate: gate[(m / gate_rpb) * gate_ld + n], or null
+    long long gate_ld;
+    int gate_rpb;
+    RowMap R;               // residual (ptr == null -> none)
+    int M, N, K;
+};
+int launch_gemm(const GemmParams& p, cudaStream_t stream);
+
+// ---- norm.cu ---------------------------------------------------------------------------------------------------------
+// y[m, :] = LN(x[m, :]) * w + b                       (affine; w/b may be null)
+// y[m, :] = LN(x[m, :]) * (1 + scale[b, :]) + shift[b, :]   (adaLN modulate; b = m / rows_per_batch)
+struct LayerNormParams {
+    const float* x; long long ldx;
+    float* y; long long ldy;
+    const float* weight; const float* bias;
+    const float* shift; const float* scale; long long mod_ld; int rows_per_batch;
+    int rows, dim;
+    float eps;
+};
+int launch_layernorm(const LayerNormParams& p, cudaStream_t stream);
+
+// ---- attention.cu ----------------------------------------------------------------------------------------------------
+enum MaskMode : int { MASK_NONE = 0, MASK_CAUSAL = 1, MASK_BAND = 2, MASK_DENSE = 3 };
+struct AttentionParams {
+    // token-major operands: element (b, t, h, d) at ptr + b*bstride + t*ld + h*64 + d ; head_dim is fixed at 64
+    const float* q; long long q_ld, q_bs;
+    const float* k; long long k_ld, k_bs;
+    const float* v; long long v_ld, v_bs;
+    float* o; long long o_ld, o_bs;
+    int B, H, Tq, Tk;
+    float scale;                   // multiplies q.k (1.0 when q is pre-scaled like HF Whisper)
+    int mask_mode;
+    int q_pos0;                    // MASK_CAUSAL: absolute position of query row 0 (keys are absolute 0..Tk-1)
+    const unsigned char* key_valid; long long key_valid_ld;   // [B, Tk] 1 = real token (null = all valid)
+    int band;                      // MASK_BAND: query r sees key c iff c - band <= r < c + band
+    const unsigned char* dense;    // MASK_DENSE: [Tq, Tk] 1 = blocked
+    const int* kv_slot;            // optional: K/V batch index of batch row b (cross attention over resident encoder slots)
+};
+int launch_attention(const AttentionParams& p, cudaStream_t stream);
+
+// ---- mel.cu ----------------------------------------------------------------------------------------------------------
+struct MelPlan;   // opaque (filterbank in CSR form + twiddles on device)
+int mel_plan_create(MelPlan** out, int n_fft, int hop, int n_mels, int pad_reflect, int log_scale,
+                    const float* mel_basis_host /* [n_mels, n_fft/2+1] */);
+void mel_plan_destroy(MelPlan* p);
+// pcm [B, n_samples] (row stride pcm_ld) -> mel [B, frames, n_mels] via RowMap-like strides (frames = n_samples/hop + 1)
+int launch_mel(const MelPlan* plan, const float* pcm, long long pcm_ld, int B, int n_samples, float* mel, long long mel_ld,
+               long long mel_bs, cudaStream_t stream);
+
+}  // namespace mb200
+
+// =====================================================================================================================
+// decode.cu — the per-token path (B small): weight-streaming GEMV family, split-KV decode attention, fused
+// logits-processor chain + token selection.  All step-varying scalars live in device memory (GenState) so that one
+// captured CUDA graph replays for every token of every generate() call.
+// =====================================================================================================================
+namespace mb200 {
+
+// vocabulary flag bits (host builds vflags[vocab_in] per call; only VF_EOS changes between calls)
+enum : unsigned char { VF_EOS = 1, VF_TIMED = 2, VF_SOS = 4, VF_LB_EOS = 8, VF_BEAT = 16, VF_MANIA = 32, VF_SCROLL = 64 };
+
+struct GenState {            // device-resident, one per engine
+    int cur_len;             // tokens currently in every ids row (prompt + generated); next token goes to ids[b][cur_len]
+    int prompt_len;          // P
+    int max_length;
+    int min_new_tokens;
+    int n_finished;
+    int ticket;              // last-CTA detection in the sampling kernel
+    int all_finished;
+    int has_last_scores;
+    int step;                // decode steps since the start of this call (RNG counter)
+    int pad_[7];
+};
+
+struct SampleConfig {        // device-resident, rewritten by the host once per generate() call
+    int B;                   // un-doubled batch rows
+    int use_cfg;             // decoder rows = 2B; rows [0,B) carry the negative prompt (modeling_mapperatorinator.py:243-245)
+    float cfg_scale;
+    int V;                   // vocab_size_out
+    int ts_start, ts_end;    // time-shift id range
+    float timeshift_bias;
+    int types_first;
+    float temperature;
+    int n_cond;              // conditional temperatures (logit_processors.py:62-71), evaluated on batch row 0 only
+    float cond_temp[3]; int cond_offset[3]; int cond_flag[3];   // flag = VF_BEAT / VF_MANIA / VF_SCROLL
+    int lookback_on; int lookback_start, lookback_end;           // LookbackBiasLogitsWarper range
+    int do_sample; int top_k; float top_p;
+    unsigned long long seed;
+    int pad_id;
+    int pos_rule_cumsum;     // 0: position = index (transformers 5.x), 1: index - n_left_pad[b] (4.5x)
+    int ids_ld;              // row stride of the ids buffer
+};
+
+enum XMode : int { X_PLAIN = 0, X_LAYERNORM = 1, X_ATTN_COMBINE = 2 };
+
+struct GemvSeg {
+    float* out;              // row b at out + b * out_bs + (pos ? (cur_len - 1) * pos_stride : 0)
+    long long out_bs;
+    long long pos_stride;    // != 0: write at the cache position of the token being processed
+    int n_begin, n_end;      // output columns [n_begin, n_end) of the stacked weight
+    float alpha;
+    int act;
+};
+
+struct GemvParams {
+    int xmode;
+    const float* x; long long x_ld;                 // PLAIN / LAYERNORM input rows
+    const float* ln_w; const float* ln_b; float eps;
+    const float* part_o; const float* part_ml; int n_splits; int H;   // ATTN_COMBINE input
+    const float* W; long long ldw; const float* bias;
+    int K, N, B;
+    int nseg; GemvSeg seg[3];
+    const float* R; long long r_ld;                 // residual rows for segment 0 (null = none)
+    const GenState* st;
+};
+int launch_gemv(const GemvParams& p, cudaStream_t stream, bool pdl);
+
+struct DecAttnParams {
+    const float* q; long long q_ld;                 // [rows, d_model], already scaled
+    const float* kc; const float* vc;               // cache base for this layer
+    long long row_stride;                           // stride between cache rows / slots
+    long long tok_stride;                           // stride between tokens (d_model)
+    const int* row_slot;                            // per decoder row: which cache row/slot to read (null = row index)
+    int fixed_len;                                  // >0: number of keys (cross attention); 0: use st->cur_len
+    const GenState* st;
+    const unsigned char* key_valid; long long key_valid_ld;   // [rows, >=P] validity of prompt positions (null = all valid)
+    float* part_o; float* part_ml;                  // [rows, H, n_splits, 64], [rows, H, n_splits, 2]
+    int rows, H, n_splits, chunk;
+};
+int launch_decode_attention(const DecAttnParams& p, cudaStream_t stream, bool pdl);
+
+struct SampleParams {
+    const float* logits; long long logits_ld;       // [rows(2B if cfg), V]
+    const SampleConfig* cfg;
+    GenState* st;
+    const unsigned char* vflags;                    // [vocab_in]
+    long long* ids;                                 // [B, ids_ld] int64 like the reference's LongTensor
+    unsigned char* finished;                        // [B]
+    int* last_ts;                                   // [B] value of the last time-shift token after the last SOS-type token, -1 if none
+    float* last_scores;                             // [2, B, V] double-buffered by step parity
+    const int* n_left_pad;                          // [rows] (pos_rule_cumsum only)
+    const float* tok_emb; const float* pos_emb; int d_model;   // decoder_embedder / embed_positions
+    float* x_out; long long x_ld;                   // [rows, d_model] residual stream input of the next step
+    int rows;
+};
+int launch_sample(const SampleParams& p, int B, cudaStream_t stream, bool pdl);
+
+// one-time per call: scan the prompt for the MonotonicTimeShift state (logit_processors.py:149-166)
+int launch_prompt_scan(const long long* ids, long long ids_ld, int B, int P, const unsigned char* vflags, int ts_start, int ts_end,
+                       int* last_ts, cudaStream_t stream);
+// prefill embedding: x[b, t] = tok_emb[ids[b, t]] + pos_emb[pos(b, t)]
+int launch_embed(const long long* ids, long long ids_ld, int rows, int B_ids, int P, const int* n_left_pad, int pos_rule_cumsum,
+                 const float* tok_emb, const float* pos_emb, int d_model, float* x, cudaStream_t stream);
+
+}  // namespace mb200

@@ -143,7 +143,7 @@ def model_generate(w, cfg, layout, model_kwargs: dict, generate_kwargs: dict, po
     max_length = int(gk.get("max_length", cfg.tgt_seq_len))
     pad_id = gk.get("pad_token_id", layout.pad_id)
     eos = torch.tensor(pr.eos_ids)
-    use_cfg = neg is not None
+    use_cfg = neg is not None and pr.cfg_scale > 1.0
     t0 = time.perf_counter()
     if enc is None:
         enc = W.encode(w, cfg, pcm)

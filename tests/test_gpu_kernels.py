@@ -1,0 +1,103 @@
+"""Kernel-level parity: each CUDA kernel, called through the C ABI, against plain torch fp32 on the CPU."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 4, 128), (77, 130, 388), (300, 768, 768), (257, 3667, 128), (513, 256, 600)])
+@pytest.mark.parametrize("act", ["none", "gelu", "gelu_tanh", "silu"])
+def test_gemm_epilogues(M, N, K, act):
+    from mapperatorinator_b200 import ops
+    g = _g(M * 31 + N)
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K)
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    rpb = 7
+    gate = torch.randn((M + rpb - 1) // rpb, N, generator=g)
+    ref = F.linear(a, w, bias)
+    ref = {"none": lambda x: x, "gelu": F.gelu, "gelu_tanh": lambda x: F.gelu(x, approximate="tanh"), "silu": F.silu}[act](ref) * 0.5
+    ref = res + gate.repeat_interleave(rpb, 0)[:M] * ref
+    out = ops.gemm(a.cuda(), w.cuda(), bias.cuda(), act, 0.5, res.cuda(), gate.cuda(), rpb).cpu()
+    assert torch.allclose(out, ref, rtol=2e-5, atol=2e-5), (out - ref).abs().max()
+
+
+@pytest.mark.parametrize("dim", [128, 768, 1024])
+def test_layernorm_affine_and_modulate(dim):
+    from mapperatorinator_b200 import ops
+    g = _g(dim)
+    x = torch.randn(37, dim, generator=g) * 3 + 1
+    w, b = torch.randn(dim, generator=g), torch.randn(dim, generator=g)
+    ref = F.layer_norm(x, (dim,), w, b, 1e-5)
+    out = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), eps=1e-5).cpu()
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+    rpb = 10
+    sh, sc = torch.randn(4, dim, generator=g), torch.randn(4, dim, generator=g)
+    ref = F.layer_norm(x, (dim,), eps=1e-6) * (1 + sc.repeat_interleave(rpb, 0)[:37]) + sh.repeat_interleave(rpb, 0)[:37]
+    out = ops.layernorm(x.cuda(), shift=sh.cuda(), scale=sc.cuda(), rows_per_batch=rpb, eps=1e-6).cpu()
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def _ref_attn(q, k, v, H, allowed):
+    B, Tq, D = q.shape
+    sp = lambda z: z.view(B, -1, H, 64).transpose(1, 2)
+    s = sp(q) @ sp(k).transpose(2, 3)
+    s = s.masked_fill(~allowed[:, None], float("-inf"))
+    p = torch.nan_to_num(torch.softmax(s, -1), nan=0.0)
+    return (p @ sp(v)).transpose(1, 2).reshape(B, Tq, D)
+
+
+@pytest.mark.parametrize("Tq,Tk", [(64, 64), (70, 70), (512, 512), (33, 512), (300, 300)])
+@pytest.mark.parametrize("mode", ["none", "causal", "band", "dense"])
+def test_attention_masks(Tq, Tk, mode):
+    from mapperatorinator_b200 import ops
+    if mode in ("causal", "band", "dense") and Tq != Tk:
+        pytest.skip("square only")
+    B, H = 2, 3
+    g = _g(Tq * 7 + Tk)
+    q, k, v = (torch.randn(B, t, H * 64, generator=g) * 0.5 for t in (Tq, Tk, Tk))
+    r, c = torch.arange(Tq)[:, None], torch.arange(Tk)[None, :]
+    allowed = torch.ones(B, Tq, Tk, dtype=torch.bool)
+    kw = {}
+    if mode == "causal":
+        kvalid = torch.ones(B, Tk, dtype=torch.uint8)
+        kvalid[1, :5] = 0                                    # left padding on row 1 (fully masked pad queries -> 0)
+        allowed = (c <= r)[None] & kvalid.bool()[:, None, :]
+        kw = dict(key_valid=kvalid.cuda())
+    elif mode == "band":
+        w = 128 if Tq > 200 else 17
+        allowed = ((r >= c - w) & (r < c + w))[None].expand(B, -1, -1)
+        kw = dict(band=w)
+    elif mode == "dense":
+        dm = torch.rand(Tq, Tk, generator=g) < 0.3
+        dm[torch.arange(Tq), torch.arange(Tq)] = False
+        allowed = (~dm)[None].expand(B, -1, -1)
+        kw = dict(dense_mask=dm.to(torch.uint8).cuda())
+    ref = _ref_attn(q, k, v, H, allowed)
+    out = ops.attention(q.cuda(), k.cuda(), v.cuda(), H, 1.0, mode, 0, **kw).cpu()
+    assert torch.allclose(out, ref, rtol=2e-5, atol=2e-5), (out - ref).abs().max()
+
+
+@pytest.mark.parametrize("flavour", ["nnAudio", "torchaudio", "torchaudio_log_reflect"])
+@pytest.mark.parametrize("n_samples", [130944, 128 * 37])
+def test_mel_vs_oracle(flavour, n_samples):
+    from mapperatorinator_b200 import MelConfig
+    from mapperatorinator_b200.engine import MelEngine
+    from oracle import mel as mo
+    cfg = {"nnAudio": MelConfig(), "torchaudio": MelConfig("torchaudio", n_mels=80),
+           "torchaudio_log_reflect": MelConfig("torchaudio", True, n_mels=128, f_min=20, pad_mode="reflect")}[flavour]
+    g = _g(n_samples)
+    t = torch.arange(n_samples) / 16000.0
+    pcm = 0.3 * torch.sin(2 * math.pi * 440 * t)[None] + 0.05 * torch.randn(3, n_samples, generator=g)
+    ref = mo.mel_forward(pcm, cfg)
+    out = MelEngine(cfg).forward(pcm.cuda()).cpu()
+    assert out.shape == ref.shape
+    scale = ref.abs().max()
+    assert (out - ref).abs().max() <= 2e-5 * scale + 1e-6, ((out - ref).abs().max(), scale)
