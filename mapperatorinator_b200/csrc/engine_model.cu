@@ -65,6 +65,7 @@ struct mb200_model {
     int* h_flag = nullptr;              // pinned
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (rows, n_splits_self) -> token-step graph
     bool use_pdl = false;
+    cudaStream_t cap_stream = nullptr;
 
     int d() const { return cfg.d_model; }
     int Ts() const { return cfg.src_seq_len / 2; }
@@ -142,6 +143,7 @@ extern "C" int mb200_model_create(mb200_model** out, const mb200_model_config* c
 extern "C" void mb200_model_destroy(mb200_model* m) {
     if (!m) return;
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+    if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     mel_plan_destroy(m->mel);
     if (m->h_flag) cudaFreeHost(m->h_flag);
     delete m;
@@ -624,10 +626,13 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
     auto key = std::make_pair(rows, n_splits_self);
     auto it = m->graphs.find(key);
     if (it == m->graphs.end()) {
+        // capture on an engine-owned stream (the caller's stream may be the legacy default stream, which cannot capture)
         cudaGraph_t graph;
-        MB_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int s = token_step(m, rows, B, n_splits_self, st, m->use_pdl);
-        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (!m->cap_stream) MB_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+        MB_CUDA_CHECK(cudaStreamSynchronize(st));
+        MB_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int s = token_step(m, rows, B, n_splits_self, m->cap_stream, m->use_pdl);
+        cudaError_t e = cudaStreamEndCapture(m->cap_stream, &graph);
         if (s) return s;
         MB_CUDA_CHECK(e);
         cudaGraphExec_t exec;

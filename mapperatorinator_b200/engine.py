@@ -158,11 +158,9 @@ class ModelEngine:
             npn = negative_prompt.detach().cpu().numpy().astype(np.int64)
             neg_full[:, :npn.shape[1]] = npn
             neg = np.ascontiguousarray(neg_full)
-            nm_full = (msk.copy() if msk is not None else np.ones_like(ids, dtype=np.uint8))
-            if negative_mask is not None:
-                nmn = negative_mask.detach().cpu().numpy().astype(np.uint8)
-                nm_full[:, :nmn.shape[1]] = nmn
-            nmsk = np.ascontiguousarray(nm_full)
+            # the reference's negative_prompt_attention_mask is swallowed by HF generate()'s own parameter of that name
+            # (transformers generation/utils.py:2142): the negative rows run with the conditional prompt's mask.
+            nmsk = np.ascontiguousarray(msk.copy() if msk is not None else np.ones_like(ids, dtype=np.uint8))
         vflags = build_vflags(layout, eos_ids)
         slots_a = np.ascontiguousarray(np.asarray(list(slots), dtype=np.int32))
         assert slots_a.shape[0] == B

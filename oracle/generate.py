@@ -150,9 +150,10 @@ def model_generate(w, cfg, layout, model_kwargs: dict, generate_kwargs: dict, po
     if use_cfg:   # prepare_inputs_for_generation: first half carries the negative prompt
         enc2 = enc.repeat(2, 1, 1)
         ids2 = ids.repeat(2, 1); ids2[:B, :neg.shape[1]] = neg
+        # NB `negative_prompt_attention_mask` never reaches prepare_inputs_for_generation: HF `generate()` has a parameter of
+        # that exact name (transformers generation/utils.py:2142) and swallows it, so the negative-prompt rows run with the
+        # CONDITIONAL prompt's padding mask (pinned by tests/golden b2_cfg).  Mirrored, not "fixed".
         mask2 = mask.repeat(2, 1)
-        if neg_mask is not None:
-            mask2[:B, :neg_mask.shape[1]] = neg_mask.bool()
         st = W.DecoderState(w, cfg, enc2)
         logits = W.decoder_forward(st, ids2, mask2, position_rule, last_only=True)[:, -1]
     else:

@@ -1,0 +1,123 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference classes (run in the build container: needs /root/reference).
+
+TEST INFRASTRUCTURE.  Usage:  python -m oracle.make_golden
+Inputs are regenerated from seeds by the tests (torch CPU generator); only reference OUTPUTS are stored.
+Weights are `init_model_state_dict(cfg, seed)` loaded into the reference model with `load_state_dict`, so no checkpoint
+is stored either.  Every case records the library versions the outputs were produced with.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from mapperatorinator_b200 import MelConfig, TokenLayout, tiny_dit_config, tiny_model_config  # noqa: E402
+from mapperatorinator_b200.weights import init_dit_state_dict, init_model_state_dict  # noqa: E402
+from oracle import cases, ref_build  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    import transformers
+    meta = dict(torch=torch.__version__, transformers=transformers.__version__)
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_grad_enabled(False)
+
+    # ---- tokenizer layout ----
+    tok = ref_build.reference_tokenizer()
+    TokenLayout.from_tokenizer(tok).to_json(os.path.join(OUT, "tokenizer_v29.json"))
+
+    # ---- stage (i): MelSpectrogram module of the reference ----
+    ref_build.ref_import.install_stubs()
+    from osuT5.osuT5.model.spectrogram import MelSpectrogram
+    mel_out = {}
+    for name, mc in cases.MEL_CASES.items():
+        if mc.implementation != "torchaudio":
+            continue   # nnAudio is absent: that flavour is pinned only through the restated transform (parity unpinned)
+        mod = MelSpectrogram(mc.implementation, mc.log_scale, mc.sample_rate, mc.n_fft, mc.n_mels, mc.hop_length, mc.f_min, mc.f_max,
+                             mc.pad_mode)
+        mel_out[name] = mod(cases.mel_pcm()).numpy()[:, ::64, :]
+    np.savez_compressed(os.path.join(OUT, "mel_reference.npz"), **mel_out, **{f"meta_{k}": v for k, v in meta.items()})
+
+    # ---- stage (ii): tiny osuT5 through the reference model_generate ----
+    from osuT5.osuT5.inference.server import model_generate
+    gen_out = {}
+    for flavour, melc in cases.MODEL_FLAVOURS.items():
+        cfg = tiny_model_config(mel=melc)
+        model, tok2, _ = ref_build.reference_model(cfg, tok=tok, mel_impl=melc.implementation)
+        sd = init_model_state_dict(cfg, 0)
+        ref_build.load_state_dict_into_reference(model, sd)
+        pcm = cases.model_pcm(cfg, 3, 0)
+        gen_out[f"{flavour}/encoder"] = model.get_encoder()(pcm)[0].numpy()[:, ::32, :]
+        for cname, (prompt, neg, gk, seed) in cases.generate_cases().items():
+            B = prompt.shape[0]
+            mk = dict(inputs=cases.model_pcm(cfg, B, seed), decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0),
+                      negative_prompt=neg, negative_prompt_attention_mask=None if neg is None else neg.ne(0))
+            ids, stats = model_generate(model, tok2, dict(mk), dict(gk))
+            gen_out[f"{flavour}/{cname}/ids"] = ids.numpy()
+            gen_out[f"{flavour}/{cname}/counts"] = np.array(stats["generated_tokens_per_sample"])
+        ids, mask = cases.teacher_forcing_case(cfg)
+        out = model(frames=cases.model_pcm(cfg, 2, 1), decoder_input_ids=ids, decoder_attention_mask=mask)
+        gen_out[f"{flavour}/teacher_logits"] = out.logits.float().numpy()[:, ::3, ::37]
+    np.savez_compressed(os.path.join(OUT, "generate_reference.npz"), **gen_out, **{f"meta_{k}": v for k, v in meta.items()})
+
+    # ---- logits processors in isolation (reference classes, synthetic scores) ----
+    from osuT5.osuT5.inference.logit_processors import (ConditionalTemperatureLogitsWarper, LookbackBiasLogitsWarper,
+                                                        MonotonicTimeShiftLogitsProcessor, TimeshiftBias, get_beat_type_tokens,
+                                                        get_mania_type_tokens, get_scroll_speed_tokens)
+    from osuT5.osuT5.event import EventType
+    proc_out = {}
+    for cname, (ids_steps, gk) in cases.processor_cases().items():
+        chain = [MonotonicTimeShiftLogitsProcessor(tok)]
+        if gk.get("timeshift_bias", 0) != 0:
+            chain.append(TimeshiftBias(gk["timeshift_bias"], tok.event_start[EventType.TIME_SHIFT], tok.event_end[EventType.TIME_SHIFT]))
+        chain.append(ConditionalTemperatureLogitsWarper(gk["temperature"], gk["timing_temperature"], gk["mania_column_temperature"],
+                                                        gk["taiko_hit_temperature"], True, get_beat_type_tokens(tok),
+                                                        get_mania_type_tokens(tok), get_scroll_speed_tokens(tok)))
+        if gk.get("lookback_time", 0) > 0:
+            chain.append(LookbackBiasLogitsWarper(gk["lookback_time"], tok, True, "cpu"))
+        for step, ids in enumerate(ids_steps):
+            scores = cases.processor_logits(cname, step, ids.shape[0], tok.vocab_size_out)
+            for p in chain:
+                scores = p(ids, scores)
+            proc_out[f"{cname}/{step}"] = scores.numpy()
+    np.savez_compressed(os.path.join(OUT, "processors_reference.npz"), **proc_out)
+
+    # ---- stage (iii): tiny DiT + the reference GaussianDiffusion loop ----
+    from osu_diffusion.utils.diffusion import create_diffusion
+    dc = tiny_dit_config()
+    dsd = init_dit_state_dict(dc, 1)
+    m = ref_build.reference_dit(dc)
+    m.load_state_dict(dsd, strict=True)
+    dit_out = {}
+    x, c, y, noise, ip, am = cases.dit_case(dc)
+    t = torch.tensor([37, 37])
+    dit_out["forward_with_cfg"] = m.forward_with_cfg(x, t, c, y, 1.5, attn_mask=am).numpy()
+    diff = create_diffusion(timestep_respacing=[100, 0, 0, 0, 0, 0, 0, 0, 0, 0], diffusion_steps=1000, noise_schedule="squaredcos_cap_v2")
+    it = iter(noise)
+    orig = torch.randn_like
+    torch.randn_like = lambda a: next(it)
+    try:
+        z0 = x.clone()
+        dfn = lambda xx: torch.where(ip, xx, z0)
+        dit_out["p_sample_loop"] = diff.p_sample_loop(m.forward_with_cfg, x.shape, x.clone(), denoised_fn=dfn, clip_denoised=True,
+                                                      model_kwargs=dict(c=c, y=y, cfg_scale=1.0, attn_mask=am, key_padding_mask=None),
+                                                      device="cpu").numpy()
+    finally:
+        torch.randn_like = orig
+    dit_out["timestep_map"] = np.array(diff.timestep_map)
+    dit_out["schedule"] = np.stack([diff.sqrt_recip_alphas_cumprod, diff.sqrt_recipm1_alphas_cumprod, diff.posterior_log_variance_clipped,
+                                    np.log(diff.betas), diff.posterior_mean_coef1, diff.posterior_mean_coef2], 1)
+    np.savez_compressed(os.path.join(OUT, "dit_reference.npz"), **dit_out, **{f"meta_{k}": v for k, v in meta.items()})
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
