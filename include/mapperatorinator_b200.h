@@ -149,6 +149,19 @@ int mb200_dit_sample_loop(mb200_dit* d, const float* z, const float* c, const fl
                           float* out, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Measurement / tuning hooks used by bench.py (not part of the reference-facing boundary).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Number of engine kernels launched by this process so far (graph replays count every node). */
+int64_t mb200_launch_count(void);
+/* option "pdl": 1 = capture the token-step graph with programmatic dependent launch edges. */
+int mb200_model_set_option(mb200_model* m, const char* name, int32_t value);
+/* Re-runs the token step eagerly `iters` times on the state of the last generate() call with CUDA events around every
+ * decode-path launch: out_us[0..2] = device us per token in {gemv, split-KV attention, logits+sample} kernels,
+ * out_us[3] = launches per token packed as gemv*1e6 + attention*1e3 + sample. */
+int mb200_model_profile_step(mb200_model* m, int32_t rows, int32_t batch, int32_t max_length, int32_t iters, float* out_us,
+                             void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Kernel-level entry points (parity tests of the individual kernels; not needed by an integrator).
  * ------------------------------------------------------------------------------------------------------------------ */
 int mb200_op_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, const float* bias, int32_t act,

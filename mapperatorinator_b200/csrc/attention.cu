@@ -183,6 +183,7 @@ int launch_attention(const AttentionParams& p, cudaStream_t stream) {
     dim3 grid((p.Tq + TQ - 1) / TQ, p.H, p.B);
     attention_kernel<<<grid, 256, smem_bytes, stream>>>(p);
     MB_LAUNCH_CHECK();
+    ++g_launch_count;
     return 0;
 }
 

@@ -8,6 +8,8 @@
 namespace mb200 {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+long long g_launch_count = 0;
+StepProfiler g_prof;
 }  // namespace mb200
 
 using namespace mb200;
@@ -18,6 +20,7 @@ struct mb200_mel {
 };
 
 extern "C" int mb200_abi_version(void) { return MB200_ABI_VERSION; }
+extern "C" int64_t mb200_launch_count(void) { return (int64_t)g_launch_count; }
 extern "C" const char* mb200_last_error(void) { return g_last_error.c_str(); }
 
 extern "C" int mb200_mel_create(mb200_mel** out, const mb200_mel_config* cfg, const float* mel_basis) {

@@ -31,6 +31,17 @@ void set_last_error(const std::string& msg);
 
 #define MB_LAUNCH_CHECK() MB_CUDA_CHECK(cudaGetLastError())
 
+// ---- measurement hooks: every launch_* bumps the counter; the step profiler brackets decode-path launches with events ----
+extern long long g_launch_count;
+struct StepProfiler {
+    bool on = false;
+    cudaEvent_t ev[1024];
+    int cls[512];      // 0 gemv, 1 decode attention, 2 sample
+    int n = 0;
+    bool created = false;
+};
+extern StepProfiler g_prof;
+
 // ---- activation ids shared by GEMM / GEMV epilogues ------------------------------------------------------------------
 enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_SILU = 3 };
 

@@ -11,480 +11,44 @@
 // weight, activations for up to 8 batch rows staged in shared memory, fp32 accumulation in a fixed order.
 #include "common.cuh"
 #include "kernels.h"
+#include "decode_device.cuh"
 
 namespace mb200 {
 namespace {
 
-// ---------------------------------------------------------------------------------------------------------------------
-// GEMV
-// ---------------------------------------------------------------------------------------------------------------------
 template <int NB>
 __global__ void __launch_bounds__(256) gemv_kernel(GemvParams p) {
     extern __shared__ __align__(16) float xs[];   // [NB][K]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = p.K, K4 = K >> 2;
     pdl_launch_dependents();
     pdl_wait();
     const int cur_pos = p.st ? p.st->cur_len - 1 : 0;
-
     for (int b0 = 0; b0 < p.B; b0 += NB) {
-        // ---- stage the activation rows ----
-        if (p.xmode == X_LAYERNORM) {
-            for (int bb = warp; bb < NB; bb += 8) {
-                float* dst = xs + bb * K;
-                if (b0 + bb >= p.B) { for (int k = lane; k < K; k += 32) dst[k] = 0.f; continue; }
-                const float4* src = reinterpret_cast<const float4*>(p.x + (long long)(b0 + bb) * p.x_ld);
-                float4 v[8];
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    int idx = i * 32 + lane;
-                    v[i] = idx < K4 ? src[idx] : make_float4(0, 0, 0, 0);
-                    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-                }
-                const float inv = 1.0f / (float)K;
-                const float mean = warp_sum(s) * inv;
-                float q = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i * 32 + lane < K4) {
-                        float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-                        q += (a * a + b * b) + (c * c + d * d);
-                    }
-                }
-                const float rstd = rsqrtf(warp_sum(q) * inv + p.eps);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    int idx = i * 32 + lane;
-                    if (idx < K4) {
-                        float4 w = reinterpret_cast<const float4*>(p.ln_w)[idx];
-                        float4 bsv = reinterpret_cast<const float4*>(p.ln_b)[idx];
-                        float4 o;
-                        o.x = (v[i].x - mean) * rstd * w.x + bsv.x; o.y = (v[i].y - mean) * rstd * w.y + bsv.y;
-                        o.z = (v[i].z - mean) * rstd * w.z + bsv.z; o.w = (v[i].w - mean) * rstd * w.w + bsv.w;
-                        reinterpret_cast<float4*>(dst)[idx] = o;
-                    }
-                }
-            }
-        } else if (p.xmode == X_ATTN_COMBINE) {
-            // merge the split-KV partials: x[b, h*64+d] = sum_s w_s o_s[d] / sum_s w_s l_s, w_s = exp(m_s - max m)
-            for (int e = tid; e < NB * K; e += 256) {
-                int bb = e / K, c = e - bb * K, h = c >> 6, d = c & 63;
-                float val = 0.f;
-                if (b0 + bb < p.B) {
-                    const long long base = ((long long)(b0 + bb) * p.H + h) * p.n_splits;
-                    float mmax = -INFINITY;
-                    for (int s = 0; s < p.n_splits; ++s) mmax = fmaxf(mmax, p.part_ml[(base + s) * 2]);
-                    float num = 0.f, den = 0.f;
-                    for (int s = 0; s < p.n_splits; ++s) {
-                        float m = p.part_ml[(base + s) * 2], l = p.part_ml[(base + s) * 2 + 1];
-                        if (l > 0.f) {
-                            float w = expf(m - mmax);
-                            num = fmaf(w, p.part_o[(base + s) * 64 + d], num);
-                            den = fmaf(w, l, den);
-                        }
-                    }
-                    val = den > 0.f ? num / den : 0.f;
-                }
-                xs[e] = val;
-            }
-        } else {
-            for (int e = tid; e < NB * K4; e += 256) {
-                int bb = e / K4, c = e - bb * K4;
-                float4 v = make_float4(0, 0, 0, 0);
-                if (b0 + bb < p.B) v = reinterpret_cast<const float4*>(p.x + (long long)(b0 + bb) * p.x_ld)[c];
-                reinterpret_cast<float4*>(xs)[e] = v;
-            }
-        }
+        gemv_stage_x<NB>(p, b0, xs, tid, 256);
         __syncthreads();
-
-        // ---- one warp per output row ----
-        for (int n = blockIdx.x * 8 + warp; n < p.N; n += gridDim.x * 8) {
-            const float4* wrow = reinterpret_cast<const float4*>(p.W + (long long)n * p.ldw);
-            float acc[NB];
-#pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = 0.f;
-            for (int base = 0; base < K4; base += 32 * 6) {
-                float4 w[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    int idx = base + j * 32 + lane;
-                    w[j] = idx < K4 ? __ldg(wrow + idx) : make_float4(0, 0, 0, 0);
-                }
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    int idx = base + j * 32 + lane;
-                    if (idx < K4) {
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) {
-                            float4 xv = reinterpret_cast<const float4*>(xs + b * K)[idx];
-                            acc[b] = fmaf(w[j].x, xv.x, acc[b]); acc[b] = fmaf(w[j].y, xv.y, acc[b]);
-                            acc[b] = fmaf(w[j].z, xv.z, acc[b]); acc[b] = fmaf(w[j].w, xv.w, acc[b]);
-                        }
-                    }
-                }
-            }
-            float mine = 0.f;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                float s = warp_sum(acc[b]);
-                if (lane == b) mine = s;
-            }
-            if (lane < NB && b0 + lane < p.B) {
-                const int b = b0 + lane;
-                int si = 0;
-                for (int s = 1; s < p.nseg; ++s) if (n >= p.seg[s].n_begin) si = s;
-                const GemvSeg& sg = p.seg[si];
-                float v = mine;
-                if (p.bias) v += __ldg(p.bias + n);
-                v = apply_act(v, sg.act) * sg.alpha;
-                if (p.R) v += p.R[(long long)b * p.r_ld + n];
-                sg.out[(long long)b * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin)] = v;
-            }
-        }
+        for (int n = blockIdx.x * 8 + warp; n < p.N; n += gridDim.x * 8)
+            gemv_row<NB, true>(p, n, p.W + (long long)n * p.ldw, xs, b0, lane, cur_pos);
         __syncthreads();
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// split-KV decode attention (query length 1, head_dim 64)
-// ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) decode_attention_kernel(DecAttnParams p) {
-    __shared__ float sc[128];        // scores of this chunk (chunk <= 128)
+    __shared__ float sc[128];
     __shared__ float red[4][64];
     __shared__ float stat[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int s = blockIdx.x, h = blockIdx.y, r = blockIdx.z;
     pdl_launch_dependents();
     pdl_wait();
     const int L = p.fixed_len > 0 ? p.fixed_len : p.st->cur_len;
     const int P = p.st ? p.st->prompt_len : 0;
-    const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
-    const long long out_idx = ((long long)r * p.H + h) * p.n_splits + s;
-    if (k_begin >= k_end) {
-        if (tid == 0) { p.part_ml[out_idx * 2] = -INFINITY; p.part_ml[out_idx * 2 + 1] = 0.f; }
-        return;
-    }
-    const int slot = p.row_slot ? p.row_slot[r] : r;
-    const float* kb = p.kc + (long long)slot * p.row_stride + h * 64;
-    const float* vb = p.vc + (long long)slot * p.row_stride + h * 64;
-    const int nk = k_end - k_begin;
-
-    // scores: 8 lanes per key, each lane owns 8 of the 64 dims
-    const int sub = lane & 7, kq = lane >> 3;
-    const float4 q0 = *reinterpret_cast<const float4*>(p.q + (long long)r * p.q_ld + h * 64 + sub * 8);
-    const float4 q1 = *reinterpret_cast<const float4*>(p.q + (long long)r * p.q_ld + h * 64 + sub * 8 + 4);
-    for (int kk = warp * 4 + kq; kk < ((nk + 15) & ~15); kk += 16) {
-        float d = 0.f;
-        const int key = k_begin + kk;
-        if (kk < nk) {
-            const float* kr = kb + (long long)key * p.tok_stride + sub * 8;
-            float4 a = *reinterpret_cast<const float4*>(kr), b = *reinterpret_cast<const float4*>(kr + 4);
-            d = q0.x * a.x;
-            d = fmaf(q0.y, a.y, d); d = fmaf(q0.z, a.z, d); d = fmaf(q0.w, a.w, d);
-            d = fmaf(q1.x, b.x, d); d = fmaf(q1.y, b.y, d); d = fmaf(q1.z, b.z, d); d = fmaf(q1.w, b.w, d);
-        }
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
-        d += __shfl_xor_sync(0xffffffffu, d, 4);
-        if (kk < nk && sub == 0) {
-            bool ok = true;
-            if (p.key_valid && key < P) ok = p.key_valid[(long long)r * p.key_valid_ld + key] != 0;
-            sc[kk] = ok ? d : -INFINITY;
-        }
-    }
-    __syncthreads();
-    // chunk max / exp / sum (warp 0)
-    if (warp == 0) {
-        float m = -INFINITY;
-        for (int i = lane; i < nk; i += 32) m = fmaxf(m, sc[i]);
-        m = warp_max(m);
-        float l = 0.f;
-        for (int i = lane; i < nk; i += 32) {
-            float pv = (sc[i] == -INFINITY) ? 0.f : expf(sc[i] - m);
-            sc[i] = pv;
-            l += pv;
-        }
-        l = warp_sum(l);
-        if (lane == 0) { stat[0] = m; stat[1] = l; }
-    }
-    __syncthreads();
-    // o = sum_k p_k V_k : warp w takes keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1
-    float2 o = make_float2(0.f, 0.f);
-    for (int kk = warp; kk < nk; kk += 4) {
-        const float pv = sc[kk];
-        const float2 vv = *reinterpret_cast<const float2*>(vb + (long long)(k_begin + kk) * p.tok_stride + lane * 2);
-        o.x = fmaf(pv, vv.x, o.x);
-        o.y = fmaf(pv, vv.y, o.y);
-    }
-    red[warp][lane * 2] = o.x;
-    red[warp][lane * 2 + 1] = o.y;
-    __syncthreads();
-    if (tid < 64) {
-        float v = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-        p.part_o[out_idx * 64 + tid] = v;
-        if (tid == 0) { p.part_ml[out_idx * 2] = stat[0]; p.part_ml[out_idx * 2 + 1] = stat[1]; }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// fused logits-processor chain + token selection
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int SAMPLE_THREADS = 512;
-constexpr int VMAX = 4096;
-
-__device__ float block_reduce(float v, bool is_max, float* scratch) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    v = is_max ? warp_max(v) : warp_sum(v);
-    __syncthreads();
-    if (lane == 0) scratch[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        float t = lane < SAMPLE_THREADS / 32 ? scratch[lane] : (is_max ? -INFINITY : 0.f);
-        t = is_max ? warp_max(t) : warp_sum(t);
-        if (lane == 0) scratch[32] = t;
-    }
-    __syncthreads();
-    return scratch[32];
-}
-
-__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
+    decode_attention_body<4>(p, blockIdx.x, blockIdx.y, blockIdx.z, L, P, sc, red, stat, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleParams p) {
-    __shared__ float s[VMAX];
-    __shared__ int sidx[VMAX];
-    __shared__ float scratch[34];
-    __shared__ int chosen_sh;
-    const int tid = threadIdx.x;
-    const int b = blockIdx.x;
+    __shared__ SampleSmem sm;
     pdl_launch_dependents();
     pdl_wait();
-    const SampleConfig& c = *p.cfg;
-    GenState* st = p.st;
-    if (st->all_finished) return;   // replays past the end of a call are no-ops (uniform across the grid)
-    const int V = c.V, B = c.B;
-    const int L = st->cur_len;
-    long long* ids_row = p.ids + (long long)b * c.ids_ld;
-    const bool suppress_eos = st->min_new_tokens > 0 && (L - st->prompt_len) < st->min_new_tokens;
-
-    // (0)+(1): min_new_tokens EOS suppression, then classifier-free guidance on raw logits
-    for (int v = tid; v < V; v += SAMPLE_THREADS) {
-        float x;
-        const bool eos = (p.vflags[v] & VF_EOS) != 0;
-        if (c.use_cfg) {
-            float cond = p.logits[(long long)b * p.logits_ld + v];          // first half = "conditional" in HF's processor
-            float unc = p.logits[(long long)(B + b) * p.logits_ld + v];
-            x = (suppress_eos && eos) ? -INFINITY : unc + (cond - unc) * c.cfg_scale;
-        } else {
-            x = p.logits[(long long)b * p.logits_ld + v];
-            if (suppress_eos && eos) x = -INFINITY;
-        }
-        s[v] = x;
-    }
-    // (2) MonotonicTimeShift, (3) TimeshiftBias, (4) temperature (decided on batch row 0)
-    const int lts = p.last_ts[b];
-    float temp = c.temperature;
-    if (c.types_first) {
-        for (int i = 0; i < c.n_cond; ++i) {
-            const int off = c.cond_offset[i];
-            if (L >= off) {
-                long long t0 = p.ids[L - off];   // row 0
-                if (t0 >= 0 && (p.vflags[t0] & c.cond_flag[i])) { temp = c.cond_temp[i]; break; }
-            }
-        }
-    }
-    __syncthreads();
-    for (int v = tid; v < V; v += SAMPLE_THREADS) {
-        float x = s[v];
-        if (v >= c.ts_start && v < c.ts_end) {
-            if (lts >= 0 && v < c.ts_start + lts) x = -INFINITY;
-            if (c.timeshift_bias != 0.f) x += c.timeshift_bias;
-        }
-        s[v] = x / temp;
-    }
-    __syncthreads();
-
-    // (5) LookbackBias
-    if (c.lookback_on) {
-        if (!c.types_first) {
-            for (int v = c.lookback_start + tid; v < c.lookback_end; v += SAMPLE_THREADS) s[v] = -INFINITY;
-            __syncthreads();
-        } else {
-            float* ls_cur = p.last_scores + ((long long)(st->step & 1) * B + b) * V;
-            const float* ls_prev = p.last_scores + ((long long)((st->step + 1) & 1) * B + b) * V;
-            for (int v = tid; v < V; v += SAMPLE_THREADS) ls_cur[v] = s[v];
-            const long long last_tok = L > 0 ? ids_row[L - 1] : -1;
-            const bool timed = last_tok >= 0 && (p.vflags[last_tok] & VF_TIMED);
-            if (st->has_last_scores && timed) {
-                float m_last = -INFINITY, m_cur = -INFINITY;
-                for (int v = tid; v < V; v += SAMPLE_THREADS) { m_last = fmaxf(m_last, ls_prev[v]); m_cur = fmaxf(m_cur, s[v]); }
-                m_last = block_reduce(m_last, true, scratch);
-                m_cur = block_reduce(m_cur, true, scratch);
-                float z_last = 0.f, z_cur = 0.f, e_last = 0.f, o_cur = 0.f;
-                for (int v = tid; v < V; v += SAMPLE_THREADS) {
-                    float pl = expf(ls_prev[v] - m_last);
-                    float pc = expf(s[v] - m_cur);
-                    z_last += pl; z_cur += pc;
-                    if (p.vflags[v] & VF_LB_EOS) e_last += pl;
-                    if (!(v >= c.lookback_start && v < c.lookback_end)) o_cur += pc;
-                }
-                z_last = block_reduce(z_last, false, scratch);
-                z_cur = block_reduce(z_cur, false, scratch);
-                e_last = block_reduce(e_last, false, scratch);
-                o_cur = block_reduce(o_cur, false, scratch);
-                const float prob_eos = e_last / z_last;
-                const float prob_event = 1.f - prob_eos;
-                const float sc = 1.f / ((o_cur / z_cur) * prob_event + prob_eos);
-                const float extra = fminf(fmaxf((sc - 1.f) * prob_eos / prob_event, 0.f), 1.f);
-                for (int v = tid; v < V; v += SAMPLE_THREADS) {
-                    float pr;
-                    if (v == c.lookback_start) pr = extra;
-                    else if (v >= c.lookback_start && v < c.lookback_end) pr = 0.f;
-                    else pr = (expf(s[v] - m_cur) / z_cur) * sc;
-                    s[v] = logf(pr);
-                }
-            }
-            __syncthreads();
-        }
-    }
-
-    // (6)-(7) selection
-    int chosen = 0;
-    if (!c.do_sample) {
-        // argmax, first index on ties (torch.argmax)
-        float best = -INFINITY; int bi = 0x7fffffff;
-        for (int v = tid; v < V; v += SAMPLE_THREADS) {
-            float x = s[v];
-            if (x > best || (x == best && v < bi)) { best = x; bi = v; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        __shared__ float wb[SAMPLE_THREADS / 32];
-        __shared__ int wi[SAMPLE_THREADS / 32];
-        if ((tid & 31) == 0) { wb[tid >> 5] = best; wi[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
-                if (wb[w] > best || (wb[w] == best && wi[w] < bi)) { best = wb[w]; bi = wi[w]; }
-            chosen_sh = (bi == 0x7fffffff) ? 0 : bi;
-        }
-        __syncthreads();
-        chosen = chosen_sh;
-    } else {
-        // sort ascending (bitonic over VMAX slots, padding = +inf at the top so real entries keep ascending order)
-        for (int v = tid; v < VMAX; v += SAMPLE_THREADS) { sidx[v] = v; if (v >= V) s[v] = INFINITY; }
-        __syncthreads();
-        const bool need_sort = c.top_k > 0 || c.top_p < 1.0f;
-        if (need_sort) {
-            for (int k = 2; k <= VMAX; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < VMAX; i += SAMPLE_THREADS) {
-                        int ixj = i ^ j;
-                        if (ixj > i) {
-                            bool up = (i & k) == 0;
-                            float a = s[i], bq = s[ixj];
-                            int ia = sidx[i], ib = sidx[ixj];
-                            bool gt = a > bq || (a == bq && ia > ib);
-                            if (gt == up) { s[i] = bq; s[ixj] = a; sidx[i] = ib; sidx[ixj] = ia; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            // real entries are now s[0..V-1] ascending
-            if (c.top_k > 0) {
-                int kk = min(c.top_k, V);
-                float thr = s[V - kk];
-                __syncthreads();
-                for (int v = tid; v < V; v += SAMPLE_THREADS) if (s[v] < thr) s[v] = -INFINITY;
-                __syncthreads();
-            }
-        }
-        // softmax over the (possibly sorted) entries
-        float m = -INFINITY;
-        for (int v = tid; v < V; v += SAMPLE_THREADS) m = fmaxf(m, s[v]);
-        m = block_reduce(m, true, scratch);
-        float z = 0.f;
-        for (int v = tid; v < V; v += SAMPLE_THREADS) z += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m);
-        z = block_reduce(z, false, scratch);
-        // serial inclusive scan by one warp-strided pass is overkill for V<=4096: thread 0 walks (V adds) — negligible vs
-        // a decoder step, and gives a fixed summation order.
-        if (tid == 0) {
-            float keep_from = 0;   // index of first kept entry for top-p
-            int first_keep = 0;
-            if (need_sort && c.top_p < 1.0f) {
-                float cum = 0.f;
-                const float cut = 1.0f - c.top_p;
-                for (int v = 0; v < V - 1; ++v) {     // the last (largest) entry is always kept (min_tokens_to_keep = 1)
-                    cum += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m) / z;
-                    if (cum <= cut) first_keep = v + 1; else break;
-                }
-            }
-            (void)keep_from;
-            float zk = 0.f;
-            for (int v = first_keep; v < V; ++v) zk += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m);
-            unsigned long long r = splitmix64(c.seed ^ splitmix64(((unsigned long long)st->step << 20) ^ (unsigned long long)b));
-            float u = (float)((r >> 40) + 0.5) * (1.0f / 16777216.0f) * zk;
-            float cum = 0.f;
-            int pick = V - 1;
-            for (int v = first_keep; v < V; ++v) {
-                cum += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m);
-                if (cum >= u) { pick = v; break; }
-            }
-            chosen_sh = sidx[pick];
-        }
-        __syncthreads();
-        chosen = chosen_sh;
-    }
-
-    // (8) finished rows emit pad; append; EOS test; state updates; next-step embedding
-    const bool was_finished = p.finished[b] != 0;
-    const long long tok = was_finished ? (long long)c.pad_id : (long long)chosen;
-    __syncthreads();
-    if (tid == 0) {
-        ids_row[L] = tok;
-        bool fin = was_finished || ((p.vflags[tok] & VF_EOS) != 0) || (L + 1 >= st->max_length);
-        if (fin && !was_finished) { p.finished[b] = 1; atomicAdd(&st->n_finished, 1); }
-        // MonotonicTimeShift state (logit_processors.py:149-166): last time shift after the last SOS-type token
-        const unsigned char fl = p.vflags[tok];
-        if (fl & VF_SOS) p.last_ts[b] = -1;
-        else if (tok >= c.ts_start && tok < c.ts_end) p.last_ts[b] = (int)(tok - c.ts_start);
-    }
-    // embedding of the token just appended, for every decoder row fed with it
-    const int nrep = c.use_cfg ? 2 : 1;
-    for (int rep = 0; rep < nrep; ++rep) {
-        const int row = rep * B + b;
-        int pos = L;
-        if (c.pos_rule_cumsum && p.n_left_pad) pos = L - p.n_left_pad[row];
-        const float4* te = reinterpret_cast<const float4*>(p.tok_emb + tok * p.d_model);
-        const float4* pe = reinterpret_cast<const float4*>(p.pos_emb + (long long)pos * p.d_model);
-        float4* xo = reinterpret_cast<float4*>(p.x_out + (long long)row * p.x_ld);
-        for (int i = tid; i < p.d_model / 4; i += SAMPLE_THREADS) {
-            float4 a = te[i], q = pe[i];
-            xo[i] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(&st->ticket, 1) == B - 1) {
-            st->ticket = 0;
-            st->cur_len = L + 1;
-            st->step = st->step + 1;
-            st->has_last_scores = 1;
-            if (st->n_finished >= B || L + 1 >= st->max_length) st->all_finished = 1;
-            __threadfence();
-        }
-    }
+    if (p.st->all_finished) return;   // replays past the end of a call are no-ops (uniform across the grid)
+    sample_body(p, blockIdx.x, sm);
 }
 
 __global__ void prompt_scan_kernel(const long long* ids, long long ids_ld, int P, const unsigned char* vflags, int ts_start, int ts_end,
@@ -515,6 +79,8 @@ __global__ void embed_kernel(const long long* ids, long long ids_ld, int P, cons
     }
 }
 
+static int g_prof_class = 0;
+
 template <typename Kern, typename Params>
 int launch_with_attrs(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, const Params& p) {
     cudaLaunchConfig_t cfg = {};
@@ -525,7 +91,11 @@ int launch_with_attrs(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
+    ++g_launch_count;
+    const bool prof = g_prof.on && g_prof.n < 512;
+    if (prof) MB_CUDA_CHECK(cudaEventRecord(g_prof.ev[2 * g_prof.n], stream));
     MB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+    if (prof) { MB_CUDA_CHECK(cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], stream)); g_prof.cls[g_prof.n++] = g_prof_class; }
     return 0;
 }
 
@@ -548,6 +118,7 @@ int launch_gemv(const GemvParams& p, cudaStream_t stream, bool pdl) {
         configured = true;
     }
     MB_REQUIRE(smem <= 200 * 1024, "GEMV activation tile does not fit shared memory");
+    g_prof_class = 0;
     switch (nb) {
         case 1: return launch_with_attrs(gemv_kernel<1>, dim3(blocks), dim3(256), smem, stream, pdl, p);
         case 2: return launch_with_attrs(gemv_kernel<2>, dim3(blocks), dim3(256), smem, stream, pdl, p);
@@ -559,10 +130,12 @@ int launch_gemv(const GemvParams& p, cudaStream_t stream, bool pdl) {
 int launch_decode_attention(const DecAttnParams& p, cudaStream_t stream, bool pdl) {
     MB_REQUIRE(p.chunk > 0 && p.chunk <= 128, "decode attention chunk must be in (0, 128]");
     if (p.rows <= 0) return 0;
+    g_prof_class = 1;
     return launch_with_attrs(decode_attention_kernel, dim3(p.n_splits, p.H, p.rows), dim3(128), 0, stream, pdl, p);
 }
 
 int launch_sample(const SampleParams& p, int B, cudaStream_t stream, bool pdl) {
+    g_prof_class = 2;
     return launch_with_attrs(sample_kernel, dim3(B), dim3(SAMPLE_THREADS), 0, stream, pdl, p);
 }
 
@@ -570,6 +143,7 @@ int launch_prompt_scan(const long long* ids, long long ids_ld, int B, int P, con
                        int* last_ts, cudaStream_t stream) {
     prompt_scan_kernel<<<B, 32, 0, stream>>>(ids, ids_ld, P, vflags, ts_start, ts_end, last_ts);
     MB_LAUNCH_CHECK();
+    ++g_launch_count;
     return 0;
 }
 
@@ -579,6 +153,7 @@ int launch_embed(const long long* ids, long long ids_ld, int rows, int B_ids, in
     if (rows <= 0 || P <= 0) return 0;
     embed_kernel<<<dim3(P, rows), 128, 0, stream>>>(ids, ids_ld, P, n_left_pad, pos_rule_cumsum, tok_emb, pos_emb, d_model, x);
     MB_LAUNCH_CHECK();
+    ++g_launch_count;
     return 0;
 }
 

@@ -63,9 +63,15 @@ struct mb200_model {
     DevBuf d_x, d_q, d_h, d_parto, d_partml, d_logits;   // decode step
     DevBuf g_state, g_cfg, g_vflags, g_ids, g_prefill_ids, g_keyvalid, g_leftpad, g_rowslot, g_finished, g_lastts, g_lastscores;
     int* h_flag = nullptr;              // pinned
-    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (rows, n_splits_self) -> token-step graph
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    std::map<std::pair<int, int>, long long> graph_nodes;   // (rows, n_splits_self) -> token-step graph
     bool use_pdl = false;
     cudaStream_t cap_stream = nullptr;
+    // persistent megakernel path
+    bool use_mega = true;
+    int num_sms = 0;
+    DevBuf g_megasync;                  // [0] grid-barrier counter, [8] error flag
+    std::map<std::pair<int, int>, std::pair<DevBuf*, int>> mega_phases;   // (rows, n_splits_self) -> device phase table
 
     int d() const { return cfg.d_model; }
     int Ts() const { return cfg.src_seq_len / 2; }
@@ -136,6 +142,13 @@ extern "C" int mb200_model_create(mb200_model** out, const mb200_model_config* c
                             mel_basis_host);
     if (s) { delete m; return s; }
     if (cudaMallocHost(&m->h_flag, 64) != cudaSuccess) { delete m; set_last_error("cudaMallocHost failed"); return 1; }
+    {
+        int dev = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (!coop) m->num_sms = 0;
+    }
     *out = m;
     return 0;
 }
@@ -459,12 +472,16 @@ static GemvParams gemv_base(int xmode, const float* W, long long ldw, const floa
     return g;
 }
 
-static int final_logits(mb200_model* m, int rows, const float* x, long long x_ld, cudaStream_t st, bool pdl) {
+static GemvParams final_logits_params(mb200_model* m, int rows, const float* x, long long x_ld) {
     const auto& c = m->cfg;
     GemvParams g = gemv_base(X_LAYERNORM, m->proj_out, c.d_model, nullptr, c.d_model, c.vocab_size_out, rows, m->g_state.as<GenState>());
     g.x = x; g.x_ld = x_ld; g.ln_w = m->dec_ln_w; g.ln_b = m->dec_ln_b;
     g.seg[0].out = m->d_logits.as<float>(); g.seg[0].out_bs = c.vocab_size_out;
-    return launch_gemv(g, st, pdl);
+    return g;
+}
+
+static int final_logits(mb200_model* m, int rows, const float* x, long long x_ld, cudaStream_t st, bool pdl) {
+    return launch_gemv(final_logits_params(m, rows, x, x_ld), st, pdl);
 }
 
 static SampleParams sample_params(mb200_model* m, int rows) {
@@ -479,7 +496,20 @@ static SampleParams sample_params(mb200_model* m, int rows) {
     return s;
 }
 
-static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaStream_t st, bool pdl) {
+// Either launches the 98 micro-phases of one token on `st` (eager / graph capture), or — when `collect` is given — records
+// them as phase descriptors for the persistent megakernel.  One definition, so both paths run the same arithmetic.
+static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaStream_t st, bool pdl,
+                      std::vector<MegaPhase>* collect = nullptr) {
+    auto emit_gemv = [&](const GemvParams& g) -> int {
+        if (!collect) return launch_gemv(g, st, pdl);
+        MegaPhase ph{}; ph.kind = 0; ph.g = g; collect->push_back(ph);
+        return 0;
+    };
+    auto emit_attn = [&](const DecAttnParams& a) -> int {
+        if (!collect) return launch_decode_attention(a, st, pdl);
+        MegaPhase ph{}; ph.kind = 1; ph.a = a; collect->push_back(ph);
+        return 0;
+    };
     const auto& c = m->cfg;
     const int d = c.d_model, f = c.ffn_dim, H = c.heads, T = c.src_seq_len / 2;
     const GenState* gs = m->g_state.as<GenState>();
@@ -498,56 +528,101 @@ static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaSt
             g.seg[0] = GemvSeg{q, d, 0, 0, d, 1.f, ACT_NONE};
             g.seg[1] = GemvSeg{skv, self_row, 2 * d, d, 2 * d, 1.f, ACT_NONE};
             g.seg[2] = GemvSeg{skv + d, self_row, 2 * d, 2 * d, 3 * d, 1.f, ACT_NONE};
-            MB_TRY(launch_gemv(g, st, pdl));
+            MB_TRY(emit_gemv(g));
         }
         {
             DecAttnParams a{};
             a.q = q; a.q_ld = d; a.kc = skv; a.vc = skv + d; a.row_stride = self_row; a.tok_stride = 2 * d; a.row_slot = nullptr;
             a.fixed_len = 0; a.st = gs; a.key_valid = m->g_keyvalid.as<unsigned char>(); a.key_valid_ld = c.tgt_seq_len;
             a.part_o = po; a.part_ml = pml; a.rows = rows; a.H = H; a.n_splits = n_splits_self; a.chunk = chunk;
-            MB_TRY(launch_decode_attention(a, st, pdl));
+            MB_TRY(emit_attn(a));
         }
         {   // combine -> out_proj + residual
             GemvParams g = gemv_base(X_ATTN_COMBINE, w.wo, d, w.bo, d, d, rows, gs);
             g.part_o = po; g.part_ml = pml; g.n_splits = n_splits_self; g.H = H;
             g.seg[0].out = x; g.seg[0].out_bs = d; g.R = x; g.r_ld = d;
-            MB_TRY(launch_gemv(g, st, pdl));
+            MB_TRY(emit_gemv(g));
         }
         {   // LN2 -> cross q
             GemvParams g = gemv_base(X_LAYERNORM, w.wq_c, d, w.bq_c, d, d, rows, gs);
             g.x = x; g.x_ld = d; g.ln_w = w.ln2_w; g.ln_b = w.ln2_b;
             g.seg[0].out = q; g.seg[0].out_bs = d;
-            MB_TRY(launch_gemv(g, st, pdl));
+            MB_TRY(emit_gemv(g));
         }
         {
             DecAttnParams a{};
             a.q = q; a.q_ld = d; a.kc = ckv; a.vc = ckv + d; a.row_stride = (long long)T * 2 * d; a.tok_stride = 2 * d;
             a.row_slot = m->g_rowslot.as<int>(); a.fixed_len = T; a.st = gs; a.key_valid = nullptr;
             a.part_o = po; a.part_ml = pml; a.rows = rows; a.H = H; a.n_splits = n_splits_cross; a.chunk = chunk;
-            MB_TRY(launch_decode_attention(a, st, pdl));
+            MB_TRY(emit_attn(a));
         }
         {
             GemvParams g = gemv_base(X_ATTN_COMBINE, w.wo_c, d, w.bo_c, d, d, rows, gs);
             g.part_o = po; g.part_ml = pml; g.n_splits = n_splits_cross; g.H = H;
             g.seg[0].out = x; g.seg[0].out_bs = d; g.R = x; g.r_ld = d;
-            MB_TRY(launch_gemv(g, st, pdl));
+            MB_TRY(emit_gemv(g));
         }
         {   // LN3 -> fc1 + GELU
             GemvParams g = gemv_base(X_LAYERNORM, w.fc1_w, d, w.fc1_b, d, f, rows, gs);
             g.x = x; g.x_ld = d; g.ln_w = w.ln3_w; g.ln_b = w.ln3_b;
             g.seg[0] = GemvSeg{hh, f, 0, 0, f, 1.f, ACT_GELU_ERF};
-            MB_TRY(launch_gemv(g, st, pdl));
+            MB_TRY(emit_gemv(g));
         }
         {   // fc2 + residual
             GemvParams g = gemv_base(X_PLAIN, w.fc2_w, f, w.fc2_b, f, d, rows, gs);
             g.x = hh; g.x_ld = f;
             g.seg[0].out = x; g.seg[0].out_bs = d; g.R = x; g.r_ld = d;
-            MB_TRY(launch_gemv(g, st, pdl));
+            MB_TRY(emit_gemv(g));
         }
     }
-    MB_TRY(final_logits(m, rows, x, d, st, pdl));
+    MB_TRY(emit_gemv(final_logits_params(m, rows, x, d)));
+    if (collect) {
+        MegaPhase ph{}; ph.kind = 2; collect->push_back(ph);
+        const int n = (int)collect->size();
+        for (int i = 0; i < n; ++i) {          // next GEMV phase after i, wrapping into the next token
+            int j = (i + 1) % n;
+            while ((*collect)[j].kind != 0) j = (j + 1) % n;
+            (*collect)[i].next_gemv = j;
+        }
+        return 0;
+    }
     MB_TRY(launch_sample(sample_params(m, rows), B, st, pdl));
     return 0;
+}
+
+// The persistent path: all remaining tokens of the call in one cooperative launch (rows <= 2, weight slices must fit).
+static int run_megakernel(mb200_model* m, int rows, int B, int n_splits_self, int max_steps, cudaStream_t st) {
+    auto key = std::make_pair(rows, n_splits_self);
+    auto it = m->mega_phases.find(key);
+    if (it == m->mega_phases.end()) {
+        std::vector<MegaPhase> phases;
+        MB_TRY(token_step(m, rows, B, n_splits_self, st, false, &phases));
+        DevBuf* buf = new DevBuf();
+        MB_TRY(buf->ensure(phases.size() * sizeof(MegaPhase)));
+        MB_CUDA_CHECK(cudaMemcpy(buf->p, phases.data(), phases.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+        it = m->mega_phases.emplace(key, std::make_pair(buf, (int)phases.size())).first;
+    }
+    MB_TRY(m->g_megasync.ensure(64));
+    MB_CUDA_CHECK(cudaMemsetAsync(m->g_megasync.p, 0, 64, st));
+    MegaParams mp{};
+    mp.phases = it->second.first->as<MegaPhase>(); mp.n_phases = it->second.second; mp.first_gemv = 0;
+    mp.sample = sample_params(m, rows); mp.st = m->g_state.as<GenState>();
+    mp.sync_counter = m->g_megasync.as<unsigned int>(); mp.error_flag = m->g_megasync.as<int>() + 8;
+    mp.max_steps = max_steps;
+    MB_TRY(launch_megakernel(mp, m->num_sms, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 1, m->g_megasync.as<int>() + 8, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    MB_REQUIRE(m->h_flag[1] == 0, m->h_flag[1] == 1 ? "megakernel grid barrier timed out" : "megakernel weight copy timed out");
+    return 0;
+}
+
+static bool mega_eligible(const mb200_model* m, int rows) {
+    if (!m->use_mega || rows > 2 || m->num_sms <= 0) return false;
+    const auto& c = m->cfg;
+    const int G = m->num_sms;
+    auto fits = [&](int N, int K) { return (size_t)((N + G - 1) / G) * K <= (size_t)MEGA_WBUF_FLOATS; };
+    return c.ffn_dim <= 3072 && fits(3 * c.d_model, c.d_model) && fits(c.d_model, c.d_model) && fits(c.ffn_dim, c.d_model) &&
+           fits(c.d_model, c.ffn_dim) && fits(c.vocab_size_out, c.d_model);
 }
 
 // =====================================================================================================================
@@ -622,7 +697,18 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
     MB_TRY(final_logits(m, rows, m->p_x.as<float>() + (size_t)(P - 1) * d, (long long)P * d, st, false));
     MB_TRY(launch_sample(sample_params(m, rows), B, st, false));
 
-    // ---- token loop: one graph replay per token, flag polled every few tokens ----
+    // ---- token loop, persistent path: every remaining token in ONE cooperative launch ----
+    if (mega_eligible(m, rows) && gp->max_length - (P + 1) > 0) {
+        MB_TRY(run_megakernel(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
+        MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
+        MB_CUDA_CHECK(cudaStreamSynchronize(st));
+        const int Lm = *m->h_flag;
+        MB_CUDA_CHECK(cudaMemcpy2DAsync(out_ids, (size_t)Lm * 8, m->g_ids.p, (size_t)ids_ld * 8, (size_t)Lm * 8, B, cudaMemcpyDeviceToHost, st));
+        MB_CUDA_CHECK(cudaStreamSynchronize(st));
+        *out_len = Lm;
+        return 0;
+    }
+    // ---- token loop, graph path: one graph replay per token, flag polled every few tokens ----
     auto key = std::make_pair(rows, n_splits_self);
     auto it = m->graphs.find(key);
     if (it == m->graphs.end()) {
@@ -631,8 +717,11 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
         if (!m->cap_stream) MB_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
         MB_CUDA_CHECK(cudaStreamSynchronize(st));
         MB_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const long long before = g_launch_count;
         int s = token_step(m, rows, B, n_splits_self, m->cap_stream, m->use_pdl);
         cudaError_t e = cudaStreamEndCapture(m->cap_stream, &graph);
+        m->graph_nodes[key] = g_launch_count - before;
+        g_launch_count = before;   // captured, not launched; replays are counted below
         if (s) return s;
         MB_CUDA_CHECK(e);
         cudaGraphExec_t exec;
@@ -648,6 +737,7 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
         // no EOS is possible before min_new_tokens are out, so the first poll can wait until then
         if (gp->min_new_tokens > produced) burst = std::min(remaining, std::max(burst, gp->min_new_tokens - produced));
         for (int i = 0; i < burst; ++i) MB_CUDA_CHECK(cudaGraphLaunch(it->second, st));
+        g_launch_count += (long long)burst * m->graph_nodes[key];
         remaining -= burst; produced += burst;
         MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag, &m->g_state.as<GenState>()->all_finished, 4, cudaMemcpyDeviceToHost, st));
         MB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -708,6 +798,40 @@ extern "C" int mb200_model_set_option(mb200_model* m, const char* name, int valu
         m->use_pdl = value != 0;
         return 0;
     }
+    if (!strcmp(name, "mega")) { m->use_mega = value != 0; return 0; }
     set_last_error(std::string("unknown option ") + name);
     return 2;
+}
+
+// Measurement hook for bench.py: replays the token step EAGERLY `iters` times on the state left by the last generate() call,
+// bracketing every decode-path launch with CUDA events on the launching stream.  out_us[0..2] = device microseconds per token
+// spent in {gemv, split-KV attention, logits/sample} kernels, out_us[3] = their launch counts packed as gemv*1e6 + attn*1e3 + sample.
+extern "C" int mb200_model_profile_step(mb200_model* m, int32_t rows, int32_t B, int32_t max_length, int32_t iters, float* out_us, void* stream) {
+    MB_REQUIRE(m && m->finalized && out_us && iters >= 1, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    GenState gs{};
+    MB_CUDA_CHECK(cudaMemcpy(&gs, m->g_state.p, sizeof(gs), cudaMemcpyDeviceToHost));
+    const int cur0 = gs.prompt_len + 1;
+    double acc[3] = {0, 0, 0}; long long cnt[3] = {0, 0, 0};
+    if (!g_prof.created) { for (auto& e : g_prof.ev) MB_CUDA_CHECK(cudaEventCreate(&e)); g_prof.created = true; }
+    const int n_splits_self = (max_length + 63) / 64;
+    for (int it = 0; it < iters; ++it) {
+        gs.cur_len = cur0 + it; gs.all_finished = 0; gs.n_finished = 0; gs.ticket = 0; gs.max_length = m->cfg.tgt_seq_len; gs.min_new_tokens = 0;
+        MB_CUDA_CHECK(cudaMemcpy(m->g_state.p, &gs, sizeof(gs), cudaMemcpyHostToDevice));
+        MB_CUDA_CHECK(cudaMemset(m->g_finished.p, 0, m->max_rows));
+        g_prof.n = 0; g_prof.on = true;
+        int s = token_step(m, rows, B, n_splits_self, st, false);
+        g_prof.on = false;
+        if (s) return s;
+        MB_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int i = 0; i < g_prof.n; ++i) {
+            float ms = 0.f;
+            MB_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+            acc[g_prof.cls[i]] += ms * 1000.0; cnt[g_prof.cls[i]]++;
+        }
+    }
+    for (int c = 0; c < 3; ++c) out_us[c] = (float)(acc[c] / iters);
+    out_us[3] = (float)((cnt[0] / iters) * 1000000LL + (cnt[1] / iters) * 1000LL + (cnt[2] / iters));
+    return 0;
 }

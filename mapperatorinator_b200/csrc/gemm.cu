@@ -126,6 +126,7 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     dim3 grid((p.N + BN - 1) / BN, (unsigned)((p.M + BM - 1) / BM));
     gemm_f32_kernel<<<grid, 256, 0, stream>>>(p);
     MB_LAUNCH_CHECK();
+    ++g_launch_count;
     return 0;
 }
 

@@ -160,6 +160,25 @@ struct SampleParams {
 };
 int launch_sample(const SampleParams& p, int B, cudaStream_t stream, bool pdl);
 
+// ---- decode_mega.cu: the persistent token-loop megakernel ----------------------------------------------------------------
+constexpr int MEGA_WBUF_FLOATS = 19712;       // 77 KB weight slice per buffer (two buffers per CTA)
+struct MegaPhase {                            // one dependent micro-phase of a token (built on the host)
+    int kind;                                 // 0 GEMV, 1 split-KV attention, 2 logits chain + token selection
+    int next_gemv;                            // index of the next GEMV phase (wraps into the next token)
+    GemvParams g;
+    DecAttnParams a;
+};
+struct MegaParams {
+    const MegaPhase* phases; int n_phases; int first_gemv;
+    SampleParams sample;
+    GenState* st;
+    unsigned int* sync_counter;               // zeroed by the host before every launch
+    int* error_flag;                          // 0 ok, 1 grid-barrier timeout, 2 weight-copy timeout
+    int max_steps;
+};
+size_t mega_smem_bytes();
+int launch_megakernel(const MegaParams& mp, int grid, cudaStream_t stream);
+
 // one-time per call: scan the prompt for the MonotonicTimeShift state (logit_processors.py:149-166)
 int launch_prompt_scan(const long long* ids, long long ids_ld, int B, int P, const unsigned char* vflags, int ts_start, int ts_end,
                        int* last_ts, cudaStream_t stream);

@@ -73,6 +73,7 @@ int launch_layernorm(const LayerNormParams& p, cudaStream_t stream) {
 #undef MB_LN_CASE
     }
     MB_LAUNCH_CHECK();
+    ++g_launch_count;
     return 0;
 }
 

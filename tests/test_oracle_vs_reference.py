@@ -1,0 +1,43 @@
+"""Live pin of the oracle against the UNMODIFIED reference classes (build container only: skipped when /root/reference
+is absent, e.g. on the GPU box — there the committed tests/golden fixtures carry the same pin)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_import
+
+pytestmark = [pytest.mark.reference, pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present")]
+
+
+def test_golden_fixtures_are_reproducible(tmp_path, monkeypatch):
+    """Re-running oracle/make_golden.py reproduces the committed fixtures bit-for-bit (same image, same seeds)."""
+    import os
+    from oracle import make_golden
+    gold_dir = make_golden.OUT
+    monkeypatch.setattr(make_golden, "OUT", str(tmp_path))
+    make_golden.main()
+    for f in ("generate_reference.npz", "dit_reference.npz", "mel_reference.npz", "processors_reference.npz"):
+        a, b = np.load(os.path.join(gold_dir, f)), np.load(os.path.join(str(tmp_path), f))
+        assert sorted(a.files) == sorted(b.files)
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (f, k)
+
+
+def test_v29_dims_single_step_logits():
+    """One teacher-forced pass at full whisper-small dimensions: reference `Mapperatorinator.forward` vs the oracle."""
+    from mapperatorinator_b200 import MelConfig, v29_model_config
+    from mapperatorinator_b200.weights import init_model_state_dict
+    from oracle import ref_build, whisper as wo
+    import dataclasses
+    cfg = dataclasses.replace(v29_model_config(), mel=MelConfig("torchaudio", n_mels=80))
+    model, tok, _ = ref_build.reference_model(cfg, mel_impl="torchaudio")
+    sd = init_model_state_dict(cfg, 0)
+    ref_build.load_state_dict_into_reference(model, sd)
+    g = torch.Generator().manual_seed(0)
+    pcm = torch.randn(1, cfg.samples_per_window, generator=g) * 0.1
+    ids = torch.randint(17, cfg.vocab_size_in, (1, 12), generator=g)
+    with torch.no_grad():
+        ref = model(frames=pcm, decoder_input_ids=ids, decoder_attention_mask=ids.ne(0)).logits.float()
+        out = wo.forward_logits(sd, cfg, pcm, ids, ids.ne(0))
+    assert torch.allclose(out, ref, rtol=1e-3, atol=1e-3), (out - ref).abs().max()
+    assert torch.equal(out.argmax(-1), ref.argmax(-1))
