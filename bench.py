@@ -108,7 +108,7 @@ def run_reference(args, rank: int, world: int) -> None:
     if rank != 0:
         return
     from oracle import generate as gen_oracle
-    cores = os.cpu_count() or 1
+    cores = args.cpu_threads or min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     cfg = v29_model_config()
     layout = TokenLayout.from_json(os.path.join(ROOT, "tests", "golden", "tokenizer_v29.json"))
@@ -159,6 +159,9 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("MB200_PDL", "0")))
     ap.add_argument("--windows", type=int, default=0, help="debug: truncate the song to this many windows")
+    ap.add_argument("--mega", type=int, default=1, help="1 = persistent token-loop megakernel (default), 0 = CUDA-graph replay per token")
+    ap.add_argument("--cpu-threads", type=int, default=int(os.environ.get("MB200_CPU_THREADS", "0")),
+                    help="torch threads of the CPU arm (0 = min(cores, 32): more threads only slow a batch-1 decoder down)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -185,6 +188,7 @@ def main() -> None:
     del sd
     if args.pdl:
         model.engine.set_option("pdl", 1)
+    model.engine.set_option("mega", args.mega)
     song = SongDecoder(model, layout)
     pinned = windows.pin_memory()
     resident = windows.to(dev)
@@ -270,7 +274,7 @@ def main() -> None:
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import generate as gen_oracle
-        cores = os.cpu_count() or 1
+        cores = args.cpu_threads or min(os.cpu_count() or 1, 32)
         torch.set_num_threads(cores)
         sd_cpu = init_model_state_dict(cfg, 0)
         cs, ctoks = [], 0

@@ -161,6 +161,11 @@ int mb200_model_set_option(mb200_model* m, const char* name, int32_t value);
 int mb200_model_profile_step(mb200_model* m, int32_t rows, int32_t batch, int32_t max_length, int32_t iters, float* out_us,
                              void* cuda_stream);
 
+/* options "mega" (1 = persistent token-loop megakernel for <= 2 decoder rows, default) and "mega_trace" (1 = record
+ * %globaltimer stamps of CTA 0 for every micro-phase of the 9th token); read them back as out[n_phases][6] nanoseconds:
+ * {phase start, activations staged, weights landed, (unused), math done, grid barrier passed}. */
+int mb200_model_read_trace(mb200_model* m, uint64_t* out, int32_t n_phases);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Kernel-level entry points (parity tests of the individual kernels; not needed by an integrator).
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "mb200_model_generate", "mb200_model_forward_logits",
     "mb200_dit_create", "mb200_dit_destroy", "mb200_dit_set_weight", "mb200_dit_finalize", "mb200_dit_forward_with_cfg",
     "mb200_dit_sample_loop",
-    "mb200_launch_count", "mb200_model_set_option", "mb200_model_profile_step",
+    "mb200_launch_count", "mb200_model_set_option", "mb200_model_profile_step", "mb200_model_read_trace",
     "mb200_op_gemm", "mb200_op_layernorm", "mb200_op_attention",
 ]
 
@@ -85,6 +85,7 @@ def load() -> C.CDLL:
     lib.mb200_model_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.mb200_launch_count.restype = i64
     lib.mb200_model_profile_step.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.mb200_model_read_trace.argtypes = [vp, vp, i32]
     lib.mb200_dit_create.argtypes = [C.POINTER(vp), C.POINTER(DitConfigC)]
     lib.mb200_dit_destroy.argtypes = [vp]; lib.mb200_dit_destroy.restype = None
     lib.mb200_dit_set_weight.argtypes = [vp, C.c_char_p, vp, i64]

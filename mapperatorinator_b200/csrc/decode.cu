@@ -16,17 +16,19 @@
 namespace mb200 {
 namespace {
 
+constexpr int GEMV_THREADS = 128, GEMV_WARPS = GEMV_THREADS / 32;
+
 template <int NB>
-__global__ void __launch_bounds__(256) gemv_kernel(GemvParams p) {
-    extern __shared__ __align__(16) float xs[];   // [NB][K]
+__global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(GemvParams p) {
+    extern __shared__ __align__(16) float xs[];   // [NB][K] activations, then NB*H*(n_splits+1) combine scratch
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
     pdl_wait();
     const int cur_pos = p.st ? p.st->cur_len - 1 : 0;
     for (int b0 = 0; b0 < p.B; b0 += NB) {
-        gemv_stage_x<NB>(p, b0, xs, tid, 256);
+        gemv_stage_x<NB>(p, b0, xs, xs + NB * p.K, tid, GEMV_THREADS);
         __syncthreads();
-        for (int n = blockIdx.x * 8 + warp; n < p.N; n += gridDim.x * 8)
+        for (int n = blockIdx.x * GEMV_WARPS + warp; n < p.N; n += gridDim.x * GEMV_WARPS)
             gemv_row<NB, true>(p, n, p.W + (long long)n * p.ldw, xs, b0, lane, cur_pos);
         __syncthreads();
     }
@@ -40,7 +42,8 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(DecAttnParams p) 
     pdl_wait();
     const int L = p.fixed_len > 0 ? p.fixed_len : p.st->cur_len;
     const int P = p.st ? p.st->prompt_len : 0;
-    decode_attention_body<4>(p, blockIdx.x, blockIdx.y, blockIdx.z, L, P, sc, red, stat, threadIdx.x);
+    const int r = blockIdx.z;
+    decode_attention_body<4>(p, blockIdx.x, blockIdx.y, r, p.row_slot ? p.row_slot[r] : r, L, P, sc, red, stat, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleParams p) {
@@ -107,8 +110,8 @@ int launch_gemv(const GemvParams& p, cudaStream_t stream, bool pdl) {
     MB_REQUIRE(p.xmode != X_ATTN_COMBINE || p.K == p.H * 64, "attention-combine prologue needs K == H*64");
     if (p.B <= 0 || p.N <= 0) return 0;
     int nb = p.B >= 8 ? 8 : (p.B > 4 ? 8 : (p.B > 2 ? 4 : p.B));
-    const size_t smem = (size_t)nb * p.K * sizeof(float);
-    const int blocks = (p.N + 7) / 8;
+    const size_t smem = ((size_t)nb * p.K + (p.xmode == X_ATTN_COMBINE ? (size_t)nb * p.H * (p.n_splits + 1) : 0)) * sizeof(float);
+    const int blocks = (p.N + GEMV_WARPS - 1) / GEMV_WARPS;
     static bool configured = false;
     if (!configured) {
         MB_CUDA_CHECK(cudaFuncSetAttribute(gemv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -120,10 +123,10 @@ int launch_gemv(const GemvParams& p, cudaStream_t stream, bool pdl) {
     MB_REQUIRE(smem <= 200 * 1024, "GEMV activation tile does not fit shared memory");
     g_prof_class = 0;
     switch (nb) {
-        case 1: return launch_with_attrs(gemv_kernel<1>, dim3(blocks), dim3(256), smem, stream, pdl, p);
-        case 2: return launch_with_attrs(gemv_kernel<2>, dim3(blocks), dim3(256), smem, stream, pdl, p);
-        case 4: return launch_with_attrs(gemv_kernel<4>, dim3(blocks), dim3(256), smem, stream, pdl, p);
-        default: return launch_with_attrs(gemv_kernel<8>, dim3(blocks), dim3(256), smem, stream, pdl, p);
+        case 1: return launch_with_attrs(gemv_kernel<1>, dim3(blocks), dim3(GEMV_THREADS), smem, stream, pdl, p);
+        case 2: return launch_with_attrs(gemv_kernel<2>, dim3(blocks), dim3(GEMV_THREADS), smem, stream, pdl, p);
+        case 4: return launch_with_attrs(gemv_kernel<4>, dim3(blocks), dim3(GEMV_THREADS), smem, stream, pdl, p);
+        default: return launch_with_attrs(gemv_kernel<8>, dim3(blocks), dim3(GEMV_THREADS), smem, stream, pdl, p);
     }
 }
 

@@ -16,7 +16,8 @@ __device__ __forceinline__ int ld_state(const int* p) { return __ldcg(p); }
 // activation staging for the GEMV family: xs[NB][K] <- LayerNorm(x) | merged split-KV partials | x
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NB>
-__device__ __forceinline__ void gemv_stage_x(const GemvParams& p, int b0, float* xs, int tid, int nthreads) {
+__device__ __forceinline__ void gemv_stage_x(const GemvParams& p, int b0, float* xs, float* scratch /* NB*H*(n_splits+1) */, int tid,
+                                             int nthreads) {
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int K = p.K, K4 = K >> 2;
     if (p.xmode == X_LAYERNORM) {
@@ -24,14 +25,18 @@ __device__ __forceinline__ void gemv_stage_x(const GemvParams& p, int b0, float*
             float* dst = xs + bb * K;
             if (b0 + bb >= p.B) { for (int k = lane; k < K; k += 32) dst[k] = 0.f; continue; }
             const float* src = p.x + (long long)(b0 + bb) * p.x_ld;
-            float4 v[8];
-            float s = 0.f;
+            float4 v[8], lw[8], lb[8];
+            // every load of this prologue (activations + LayerNorm affine) is issued before the first reduction: one L2 round trip
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 int idx = i * 32 + lane;
                 v[i] = idx < K4 ? ldcg4(src + idx * 4) : make_float4(0, 0, 0, 0);
-                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                lw[i] = idx < K4 ? __ldg(reinterpret_cast<const float4*>(p.ln_w) + idx) : make_float4(0, 0, 0, 0);
+                lb[i] = idx < K4 ? __ldg(reinterpret_cast<const float4*>(p.ln_b) + idx) : make_float4(0, 0, 0, 0);
             }
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
             const float inv = 1.0f / (float)K;
             const float mean = warp_sum(s) * inv;
             float q = 0.f;
@@ -47,8 +52,7 @@ __device__ __forceinline__ void gemv_stage_x(const GemvParams& p, int b0, float*
             for (int i = 0; i < 8; ++i) {
                 int idx = i * 32 + lane;
                 if (idx < K4) {
-                    float4 w = __ldg(reinterpret_cast<const float4*>(p.ln_w) + idx);
-                    float4 bsv = __ldg(reinterpret_cast<const float4*>(p.ln_b) + idx);
+                    const float4 w = lw[i], bsv = lb[i];
                     float4 o;
                     o.x = (v[i].x - mean) * rstd * w.x + bsv.x; o.y = (v[i].y - mean) * rstd * w.y + bsv.y;
                     o.z = (v[i].z - mean) * rstd * w.z + bsv.z; o.w = (v[i].w - mean) * rstd * w.w + bsv.w;
@@ -57,26 +61,78 @@ __device__ __forceinline__ void gemv_stage_x(const GemvParams& p, int b0, float*
             }
         }
     } else if (p.xmode == X_ATTN_COMBINE) {
-        // merge the split-KV partials: x[b, h*64+d] = sum_s w_s o_s[d] / sum_s w_s l_s, w_s = exp(m_s - max m)
-        for (int e = tid; e < NB * K; e += nthreads) {
-            int bb = e / K, c = e - bb * K, h = c >> 6, d = c & 63;
-            float val = 0.f;
-            if (b0 + bb < p.B) {
-                const long long base = ((long long)(b0 + bb) * p.H + h) * p.n_splits;
-                float mmax = -INFINITY;
-                for (int s = 0; s < p.n_splits; ++s) mmax = fmaxf(mmax, __ldcg(p.part_ml + (base + s) * 2));
-                float num = 0.f, den = 0.f;
-                for (int s = 0; s < p.n_splits; ++s) {
-                    float m = __ldcg(p.part_ml + (base + s) * 2), l = __ldcg(p.part_ml + (base + s) * 2 + 1);
-                    if (l > 0.f) {
-                        float w = expf(m - mmax);
-                        num = fmaf(w, __ldcg(p.part_o + (base + s) * 64 + d), num);
-                        den = fmaf(w, l, den);
+        // merge the split-KV partials: x[b, h*64+d] = sum_s w_s o_s[d] / sum_s w_s l_s, w_s = exp(m_s - max m).
+        // Stage A: one thread per (row, head) computes the split weights (independent loads, two L2 round trips);
+        // stage B: one thread per element gathers its n_splits partials with all loads in flight at once.
+        const int S = p.n_splits;
+        if (S <= 8) {
+            // single round trip: every element thread fetches its (<= 8) partials AND the (m, l) pairs of its head in one batch and
+            // derives the split weights itself (a few redundant expf beat a second dependent L2 access)
+            for (int e = tid; e < NB * K; e += nthreads) {
+                const int bb = e / K, c = e - bb * K, h = c >> 6, d = c & 63;
+                float val = 0.f;
+                if (b0 + bb < p.B) {
+                    const long long base = ((long long)(b0 + bb) * p.H + h) * S;
+                    float2 ml[8]; float po[8];
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        ml[s] = s < S ? ldcg2(p.part_ml + (base + s) * 2) : make_float2(-INFINITY, 0.f);
+                        po[s] = s < S ? __ldcg(p.part_o + (base + s) * 64 + d) : 0.f;
+                    }
+                    float mmax = -INFINITY;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) if (s < S) mmax = fmaxf(mmax, ml[s].x);
+                    float num = 0.f, den = 0.f;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        if (s < S && ml[s].y > 0.f) {
+                            const float w = expf(ml[s].x - mmax);
+                            num = fmaf(w, po[s], num);
+                            den = fmaf(w, ml[s].y, den);
+                        }
+                    }
+                    val = den > 0.f ? num / den : 0.f;
+                }
+                xs[e] = val;
+            }
+        } else {
+            for (int idx = tid; idx < NB * p.H; idx += nthreads) {
+                const int bb = idx / p.H, h = idx - bb * p.H;
+                float* wv = scratch + idx * (S + 1);
+                float den = 0.f;
+                if (b0 + bb < p.B) {
+                    const float* ml = p.part_ml + ((long long)(b0 + bb) * p.H + h) * S * 2;
+                    float mmax = -INFINITY;
+    #pragma unroll 8
+                    for (int s = 0; s < S; ++s) mmax = fmaxf(mmax, __ldcg(ml + s * 2));
+    #pragma unroll 8
+                    for (int s = 0; s < S; ++s) {
+                        const float2 v = ldcg2(ml + s * 2);
+                        const float w = v.y > 0.f ? expf(v.x - mmax) : 0.f;
+                        wv[s] = w;
+                        if (v.y > 0.f) den = fmaf(w, v.y, den);
+                    }
+                } else {
+                    for (int s = 0; s < S; ++s) wv[s] = 0.f;
+                }
+                wv[S] = den;
+            }
+            __syncthreads();
+            for (int e = tid; e < NB * K; e += nthreads) {
+                const int bb = e / K, c = e - bb * K, h = c >> 6, d = c & 63;
+                const float* wv = scratch + (bb * p.H + h) * (S + 1);
+                const float* po = p.part_o + ((long long)(b0 + bb) * p.H + h) * S * 64 + d;
+                float num = 0.f;
+                if (b0 + bb < p.B) {
+    #pragma unroll 8
+                    for (int s = 0; s < S; ++s) {
+                        const float w = wv[s];
+                        if (w != 0.f) num = fmaf(w, __ldcg(po + s * 64), num);
                     }
                 }
-                val = den > 0.f ? num / den : 0.f;
+                const float den = wv[S];
+                xs[e] = den > 0.f ? num / den : 0.f;
             }
-            xs[e] = val;
         }
     } else {
         for (int e = tid; e < NB * K4; e += nthreads) {
@@ -89,23 +145,36 @@ __device__ __forceinline__ void gemv_stage_x(const GemvParams& p, int b0, float*
 }
 
 // one output row n for NB batch rows: dot(W[n, :], xs[b, :]) with the weight row at `wrow` (global or shared memory)
+template <int NB>
+__device__ __forceinline__ void gemv_row_operands(const GemvParams& p, int n, int b0, int lane, float& bias_v, float& r_v) {
+    // epilogue operands (bias of output n, residual of (row lane, n)); fetched early so their latency hides under the dot product
+    bias_v = 0.f; r_v = 0.f;
+    if (lane < NB && b0 + lane < p.B) {
+        if (p.bias) bias_v = __ldg(p.bias + n);
+        if (p.R) r_v = __ldcg(p.R + (long long)(b0 + lane) * p.r_ld + n);
+    }
+}
+
 template <int NB, bool W_GLOBAL>
-__device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float* wrow_f, const float* xs, int b0, int lane, int cur_pos) {
+__device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float* wrow_f, const float* xs, int b0, int lane, int cur_pos,
+                                         bool have_operands = false, float bias_v = 0.f, float r_v = 0.f) {
     const int K = p.K, K4 = K >> 2;
     const float4* wrow = reinterpret_cast<const float4*>(wrow_f);
+    if (!have_operands) gemv_row_operands<NB>(p, n, b0, lane, bias_v, r_v);
     float acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.f;
-    for (int base = 0; base < K4; base += 32 * 6) {
-        float4 w[6];
+    constexpr int U = W_GLOBAL ? 12 : 6;     // float4 loads in flight per lane (same j-major summation order either way)
+    for (int base = 0; base < K4; base += 32 * U) {
+        float4 w[U];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
+        for (int j = 0; j < U; ++j) {
             int idx = base + j * 32 + lane;
             if (W_GLOBAL) w[j] = idx < K4 ? __ldg(wrow + idx) : make_float4(0, 0, 0, 0);
             else          w[j] = idx < K4 ? wrow[idx] : make_float4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
+        for (int j = 0; j < U; ++j) {
             int idx = base + j * 32 + lane;
             if (idx < K4) {
 #pragma unroll
@@ -129,9 +198,9 @@ __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float
         for (int s = 1; s < p.nseg; ++s) if (n >= p.seg[s].n_begin) si = s;
         const GemvSeg& sg = p.seg[si];
         float v = mine;
-        if (p.bias) v += __ldg(p.bias + n);
+        if (p.bias) v += bias_v;
         v = apply_act(v, sg.act) * sg.alpha;
-        if (p.R) v += __ldcg(p.R + (long long)b * p.r_ld + n);
+        if (p.R) v += r_v;
         sg.out[(long long)b * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin)] = v;
     }
 }
@@ -140,7 +209,7 @@ __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float
 // split-KV decode attention for one (split s, head h, row r); NW warps cooperate; smem: sc[128], red[NW][64], stat[2]
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NW>
-__device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, int s, int h, int r, int L, int P, float* sc,
+__device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, int s, int h, int r, int slot, int L, int P, float* sc,
                                                       float (*red)[64], float* stat, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
     const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
@@ -149,7 +218,6 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
         if (tid == 0) { p.part_ml[out_idx * 2] = -INFINITY; p.part_ml[out_idx * 2 + 1] = 0.f; }
         return;
     }
-    const int slot = p.row_slot ? p.row_slot[r] : r;
     const float* kb = p.kc + (long long)slot * p.row_stride + h * 64;
     const float* vb = p.vc + (long long)slot * p.row_stride + h * 64;
     const int nk = k_end - k_begin;
@@ -158,24 +226,44 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
     const int sub = lane & 7, kq = lane >> 3;
     const float4 q0 = ldcg4(p.q + (long long)r * p.q_ld + h * 64 + sub * 8);
     const float4 q1 = ldcg4(p.q + (long long)r * p.q_ld + h * 64 + sub * 8 + 4);
-    for (int kk = warp * 4 + kq; kk < ((nk + 4 * NW - 1) / (4 * NW)) * (4 * NW); kk += 4 * NW) {
-        float d = 0.f;
-        const int key = k_begin + kk;
+    // fixed trip count (chunk <= 128) so every K load of the chunk is in flight before the first shuffle
+    constexpr int SC_ITERS = 128 / (4 * NW);
+    float4 ka[SC_ITERS], kb4[SC_ITERS];
+    unsigned char kvalid[SC_ITERS];                      // prompt-padding validity, fetched in the same batch as K
+#pragma unroll
+    for (int it = 0; it < SC_ITERS; ++it) {
+        const int kk = it * 4 * NW + warp * 4 + kq;
+        kvalid[it] = 1;
         if (kk < nk) {
-            const float* kr = kb + (long long)key * p.tok_stride + sub * 8;
-            float4 a = ldcg4(kr), b = ldcg4(kr + 4);
-            d = q0.x * a.x;
-            d = fmaf(q0.y, a.y, d); d = fmaf(q0.z, a.z, d); d = fmaf(q0.w, a.w, d);
-            d = fmaf(q1.x, b.x, d); d = fmaf(q1.y, b.y, d); d = fmaf(q1.z, b.z, d); d = fmaf(q1.w, b.w, d);
+            const float* kr = kb + (long long)(k_begin + kk) * p.tok_stride + sub * 8;
+            ka[it] = ldcg4(kr); kb4[it] = ldcg4(kr + 4);
+            if (p.key_valid && k_begin + kk < P) kvalid[it] = p.key_valid[(long long)r * p.key_valid_ld + k_begin + kk];
+        } else {
+            ka[it] = make_float4(0, 0, 0, 0); kb4[it] = make_float4(0, 0, 0, 0);
         }
+    }
+    // V rows do not depend on the scores: fetch them now (warps 0..3, 16 keys each cover a 64-key chunk) so the whole phase
+    // costs one memory round trip instead of two
+    constexpr int PV_PRE = 16;
+    float2 vpre[PV_PRE];
+    if (warp < 4) {
+#pragma unroll
+        for (int i = 0; i < PV_PRE; ++i) {
+            const int kk = warp + 4 * i;
+            vpre[i] = kk < nk ? ldcg2(vb + (long long)(k_begin + kk) * p.tok_stride + lane * 2) : make_float2(0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < SC_ITERS; ++it) {
+        const int kk = it * 4 * NW + warp * 4 + kq;
+        const float4 a = ka[it], b = kb4[it];
+        float d = q0.x * a.x;
+        d = fmaf(q0.y, a.y, d); d = fmaf(q0.z, a.z, d); d = fmaf(q0.w, a.w, d);
+        d = fmaf(q1.x, b.x, d); d = fmaf(q1.y, b.y, d); d = fmaf(q1.z, b.z, d); d = fmaf(q1.w, b.w, d);
         d += __shfl_xor_sync(0xffffffffu, d, 1);
         d += __shfl_xor_sync(0xffffffffu, d, 2);
         d += __shfl_xor_sync(0xffffffffu, d, 4);
-        if (kk < nk && sub == 0) {
-            bool ok = true;
-            if (p.key_valid && key < P) ok = p.key_valid[(long long)r * p.key_valid_ld + key] != 0;
-            sc[kk] = ok ? d : -INFINITY;
-        }
+        if (kk < nk && sub == 0) sc[kk] = kvalid[it] ? d : -INFINITY;
     }
     __syncthreads();
     if (warp == 0) {
@@ -196,7 +284,17 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
     // whatever NW is, so the per-kernel path and the megakernel produce bit-identical partials.
     if (warp < 4) {
         float2 o = make_float2(0.f, 0.f);
-        for (int kk = warp; kk < nk; kk += 4) {
+#pragma unroll
+        for (int i = 0; i < PV_PRE; ++i) {
+            const int kk = warp + 4 * i;
+            if (kk < nk) {
+                const float pv = sc[kk];
+                o.x = fmaf(pv, vpre[i].x, o.x);
+                o.y = fmaf(pv, vpre[i].y, o.y);
+            }
+        }
+#pragma unroll 4
+        for (int kk = warp + 4 * PV_PRE; kk < nk; kk += 4) {      // chunks longer than 64 keys
             const float pv = sc[kk];
             const float2 vv = ldcg2(vb + (long long)(k_begin + kk) * p.tok_stride + lane * 2);
             o.x = fmaf(pv, vv.x, o.x);

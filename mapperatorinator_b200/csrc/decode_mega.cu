@@ -23,8 +23,8 @@ namespace {
 
 constexpr int MEGA_THREADS = SAMPLE_THREADS;            // 512
 constexpr int MEGA_WARPS = MEGA_THREADS / 32;
-constexpr int MEGA_NB = 2;                              // decoder rows handled (1 or 2)
-constexpr int XS_FLOATS = MEGA_NB * 3072;
+constexpr int MEGA_NB_MAX = 2;                          // decoder rows handled: the kernel is instantiated for 1 and 2
+constexpr int XS_FLOATS = MEGA_NB_MAX * 3072;
 
 struct __align__(16) MegaSmem {
     float wbuf[2][MEGA_WBUF_FLOATS];
@@ -33,7 +33,9 @@ struct __align__(16) MegaSmem {
         SampleSmem sample;
         struct { float sc[128]; float red[4][64]; float stat[2]; } attn;
     } u;
-    MegaPhase phase;
+    MegaPhase phase[2];
+    int ctrl[8];                                // all_finished, error, cur_len, prompt_len, encoder slot of row 0 / row 1
+    float combine[MEGA_NB_MAX * 16 * 33];           // split weights for the attention-combine prologue (H <= 16, n_splits <= 32)
     unsigned long long mbar[2];
 };
 
@@ -84,23 +86,37 @@ __device__ __forceinline__ bool wait_weights(unsigned long long* bar, unsigned p
     return false;
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define MEGA_TRACE(slot)                                                                              \
+    do {                                                                                              \
+        if (tracing && tid == 0) mp.trace[(long long)pi * 6 + (slot)] = gtimer();                     \
+    } while (0)
+
 __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int target, int* error_flag) {
+    // arrive = one fire-and-forget release reduction (cumulative over the CTA's writes through the bar.sync before it);
+    // wait = acquire polling.  One L2 round trip after the last arrival, no separate fences.
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned int v = 0;
         long long spin = 0;
         while (true) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
             if (v >= target) break;
-            if (++spin > (1ll << 26) || *reinterpret_cast<volatile int*>(error_flag) != 0) { atomicExch(error_flag, 1); break; }
+            if ((++spin & 0xFFF) == 0 && (spin > (1ll << 25) || *reinterpret_cast<volatile int*>(error_flag) != 0)) {
+                atomicExch(error_flag, 1);
+                break;
+            }
         }
-        __threadfence();
     }
     __syncthreads();
 }
 
+template <int MEGA_NB>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams mp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MegaSmem& sm = *reinterpret_cast<MegaSmem*>(smem_raw);
@@ -116,32 +132,71 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
     unsigned int g_idx = 0;          // running index of GEMV phases (selects buffer + mbarrier parity)
     unsigned int sync_target = 0;
     if (tid == 0) prefetch_weights(&mp.phases[mp.first_gemv], sm.wbuf[0], &sm.mbar[0], cta, G);
-    bool ok = true;
 
-    for (int step = 0; step < mp.max_steps && ok; ++step) {
-        if (ld_state(&mp.st->all_finished)) break;                 // uniform: written before the previous grid barrier
-        const int cur_pos = ld_state(&mp.st->cur_len) - 1;
-        const int P = ld_state(&mp.st->prompt_len);
-        for (int pi = 0; pi < mp.n_phases && ok; ++pi) {
-            // stage the phase descriptor in shared memory (immutable, so plain loads are fine)
-            {
-                const int* src = reinterpret_cast<const int*>(&mp.phases[pi]);
-                int* dst = reinterpret_cast<int*>(&sm.phase);
-                for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += MEGA_THREADS) dst[i] = src[i];
-            }
-            __syncthreads();
-            const MegaPhase& ph = sm.phase;
+    // phase descriptors are double-buffered in shared memory: slot `cur` is the phase being executed, slot `cur ^ 1` is
+    // filled with the NEXT phase's descriptor while this one runs (its latency never sits on the critical path)
+    auto load_desc = [&](int pi, int slot) {
+        const int* src = reinterpret_cast<const int*>(&mp.phases[pi]);
+        int* dst = reinterpret_cast<int*>(&sm.phase[slot]);
+        for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += MEGA_THREADS) dst[i] = src[i];
+    };
+    int cur = 0;
+    load_desc(0, 0);
+    __syncthreads();
+
+    for (int step = 0; step < mp.max_steps; ++step) {
+        // uniform across the grid: all three were written before the previous grid barrier
+        if (tid == 0) {
+            sm.ctrl[0] = ld_state(&mp.st->all_finished); sm.ctrl[1] = ld_state(mp.error_flag);
+            sm.ctrl[2] = ld_state(&mp.st->cur_len); sm.ctrl[3] = ld_state(&mp.st->prompt_len);
+            sm.ctrl[4] = mp.row_slot[0]; sm.ctrl[5] = mp.sample.rows > 1 ? mp.row_slot[1] : 0;
+        }
+        __syncthreads();
+        const int fin = sm.ctrl[0], err = sm.ctrl[1], cur_pos = sm.ctrl[2] - 1, P = sm.ctrl[3];
+        if (fin || err) break;
+        const bool tracing = mp.trace != nullptr && step == mp.trace_step && cta == 0;
+        for (int pi = 0; pi < mp.n_phases; ++pi) {
+            const MegaPhase& ph = sm.phase[cur];
+            MEGA_TRACE(0);
+            // next phase's descriptor: requested now into a register, parked in shared memory at the end of the phase, so its
+            // latency is not serialised in front of this phase's own loads
+            constexpr int DESC_WORDS = (int)(sizeof(MegaPhase) / 4);
+            static_assert(DESC_WORDS <= MEGA_THREADS, "descriptor must fit one word per thread");
+            int desc_word = 0;
+            if (tid < DESC_WORDS) desc_word = reinterpret_cast<const int*>(&mp.phases[pi + 1 < mp.n_phases ? pi + 1 : 0])[tid];
             if (ph.kind == 0) {
                 const int buf = g_idx & 1;
-                if (tid == 0) prefetch_weights(&mp.phases[ph.next_gemv], sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, G);
-                gemv_stage_x<MEGA_NB>(ph.g, 0, sm.u.xs, tid, MEGA_THREADS);
-                __syncthreads();
-                ok = wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, mp.error_flag);
                 int r0, r1;
                 cta_rows(ph.g.N, cta, G, r0, r1);
-                if (ok)
-                    for (int n = r0 + warp; n < r1; n += MEGA_WARPS)
+                // epilogue operands (bias, residual) of this warp's rows are requested first, together with the activations
+                float bias_v[4], r_v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = r0 + warp + j * MEGA_WARPS;
+                    bias_v[j] = 0.f; r_v[j] = 0.f;
+                    if (n < r1) gemv_row_operands<MEGA_NB>(ph.g, n, 0, lane, bias_v[j], r_v[j]);
+                }
+                gemv_stage_x<MEGA_NB>(ph.g, 0, sm.u.xs, sm.combine, tid, MEGA_THREADS);
+                MEGA_TRACE(1);
+                __syncthreads();
+                MEGA_TRACE(2);
+                // The next GEMV's weight slice is requested only now: measured on B200, issuing the ~5-9 MB bulk stream at
+                // the top of the phase queued this phase's few small latency-critical loads (activations, LN affine, bias)
+                // behind it and cost ~2.5 us per phase.  It still has the rest of this phase plus the next prologue to land.
+                if (tid == 0) prefetch_weights(&mp.phases[ph.next_gemv], sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, G);
+                wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, mp.error_flag);   // on a timeout the error flag ends the loop at the next token
+                MEGA_TRACE(3);
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = r0 + warp + j * MEGA_WARPS;
+                        if (n < r1)
+                            gemv_row<MEGA_NB, false>(ph.g, n, sm.wbuf[buf] + (long long)(n - r0) * ph.g.K, sm.u.xs, 0, lane, cur_pos, true,
+                                                     bias_v[j], r_v[j]);
+                    }
+                    for (int n = r0 + warp + 4 * MEGA_WARPS; n < r1; n += MEGA_WARPS)      // more than 64 rows per CTA (small K)
                         gemv_row<MEGA_NB, false>(ph.g, n, sm.wbuf[buf] + (long long)(n - r0) * ph.g.K, sm.u.xs, 0, lane, cur_pos);
+                }
                 ++g_idx;
             } else if (ph.kind == 1) {
                 const DecAttnParams& a = ph.a;
@@ -149,19 +204,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                 const int units = a.rows * a.H * a.n_splits;
                 for (int u = cta; u < units; u += G) {
                     const int s = u % a.n_splits, h = (u / a.n_splits) % a.H, r = u / (a.n_splits * a.H);
-                    decode_attention_body<MEGA_WARPS>(a, s, h, r, L, P, sm.u.attn.sc, sm.u.attn.red, sm.u.attn.stat, tid);
+                    decode_attention_body<MEGA_WARPS>(a, s, h, r, a.row_slot ? sm.ctrl[4 + r] : r, L, P, sm.u.attn.sc, sm.u.attn.red,
+                                                      sm.u.attn.stat, tid);
                     __syncthreads();
                 }
             } else {
                 if (cta < mp.sample.cfg->B) sample_body(mp.sample, cta, sm.u.sample);
             }
+            if (tid < DESC_WORDS) reinterpret_cast<int*>(&sm.phase[cur ^ 1])[tid] = desc_word;
+            __syncthreads();
+            MEGA_TRACE(4);
             sync_target += G;
             grid_sync(mp.sync_counter, sync_target, mp.error_flag);
-            if (*reinterpret_cast<volatile int*>(mp.error_flag) != 0) ok = false;
+            MEGA_TRACE(5);
+            cur ^= 1;
         }
     }
     // drain the weight prefetch that is still in flight so no bulk copy outlives the CTA
-    if (ok) wait_weights(&sm.mbar[g_idx & 1], (g_idx >> 1) & 1, mp.error_flag);
+    wait_weights(&sm.mbar[g_idx & 1], (g_idx >> 1) & 1, mp.error_flag);
 }
 
 }  // namespace
@@ -171,15 +231,18 @@ size_t mega_smem_bytes() { return sizeof(MegaSmem) + 128; }
 int launch_megakernel(const MegaParams& mp, int grid, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_bytes()));
+        int per_sm = 0;
+        MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel<2>, MEGA_THREADS, mega_smem_bytes()));
+        MB_REQUIRE(per_sm >= 1, "megakernel does not fit on an SM");
         configured = true;
     }
-    int per_sm = 0;
-    MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel, MEGA_THREADS, mega_smem_bytes()));
-    MB_REQUIRE(per_sm >= 1, "megakernel does not fit on an SM");
+    MB_REQUIRE(mp.sample.rows >= 1 && mp.sample.rows <= MEGA_NB_MAX, "megakernel handles 1 or 2 decoder rows");
     MegaParams p = mp;
     void* args[] = {&p};
-    MB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)decode_megakernel, dim3(grid), dim3(MEGA_THREADS), args, mega_smem_bytes(), stream));
+    const void* fn = mp.sample.rows == 1 ? (const void*)decode_megakernel<1> : (const void*)decode_megakernel<2>;
+    MB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(MEGA_THREADS), args, mega_smem_bytes(), stream));
     ++g_launch_count;
     return 0;
 }

@@ -71,6 +71,7 @@ struct mb200_model {
     bool use_mega = true;
     int num_sms = 0;
     DevBuf g_megasync;                  // [0] grid-barrier counter, [8] error flag
+    DevBuf mega_trace;                  // optional per-phase globaltimer stamps (option "mega_trace")
     std::map<std::pair<int, int>, std::pair<DevBuf*, int>> mega_phases;   // (rows, n_splits_self) -> device phase table
 
     int d() const { return cfg.d_model; }
@@ -608,7 +609,8 @@ static int run_megakernel(mb200_model* m, int rows, int B, int n_splits_self, in
     mp.phases = it->second.first->as<MegaPhase>(); mp.n_phases = it->second.second; mp.first_gemv = 0;
     mp.sample = sample_params(m, rows); mp.st = m->g_state.as<GenState>();
     mp.sync_counter = m->g_megasync.as<unsigned int>(); mp.error_flag = m->g_megasync.as<int>() + 8;
-    mp.max_steps = max_steps;
+    mp.max_steps = max_steps; mp.row_slot = m->g_rowslot.as<int>();
+    mp.trace = m->mega_trace.p ? m->mega_trace.as<unsigned long long>() : nullptr; mp.trace_step = 8;
     MB_TRY(launch_megakernel(mp, m->num_sms, st));
     MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 1, m->g_megasync.as<int>() + 8, 4, cudaMemcpyDeviceToHost, st));
     MB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -799,6 +801,10 @@ extern "C" int mb200_model_set_option(mb200_model* m, const char* name, int valu
         return 0;
     }
     if (!strcmp(name, "mega")) { m->use_mega = value != 0; return 0; }
+    if (!strcmp(name, "mega_trace")) {
+        if (value) { MB_TRY(m->mega_trace.ensure(128 * 6 * 8)); MB_CUDA_CHECK(cudaMemset(m->mega_trace.p, 0, 128 * 6 * 8)); }
+        return 0;
+    }
     set_last_error(std::string("unknown option ") + name);
     return 2;
 }
@@ -833,5 +839,13 @@ extern "C" int mb200_model_profile_step(mb200_model* m, int32_t rows, int32_t B,
     }
     for (int c = 0; c < 3; ++c) out_us[c] = (float)(acc[c] / iters);
     out_us[3] = (float)((cnt[0] / iters) * 1000000LL + (cnt[1] / iters) * 1000LL + (cnt[2] / iters));
+    return 0;
+}
+
+// debug: copy the megakernel phase trace (option "mega_trace") to host: out[n_phases][6] nanosecond stamps
+extern "C" int mb200_model_read_trace(mb200_model* m, uint64_t* out, int32_t n_phases) {
+    MB_REQUIRE(m && out && m->mega_trace.p && n_phases <= 128, "trace not enabled");
+    MB_CUDA_CHECK(cudaDeviceSynchronize());
+    MB_CUDA_CHECK(cudaMemcpy(out, m->mega_trace.p, (size_t)n_phases * 6 * 8, cudaMemcpyDeviceToHost));
     return 0;
 }

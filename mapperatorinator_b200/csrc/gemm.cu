@@ -115,6 +115,78 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_kernel(GemmParams p) {
     }
 }
 
+// ---- skinny variant: M <= 64 rows (decoder prefill of a 17-50 token prompt) ------------------------------------------------
+// The 128x128 tile kernel above would run such a problem on N/128 = 6..24 CTAs with a latency-bound K loop (measured 115 us
+// per projection, 11.5 ms per prefill).  Here the weight matrix is the streamed operand: one CTA owns 16 weight rows, lanes
+// own the (<= 64) activation rows, the activation chunk sits transposed in shared memory and every weight value is a
+// shared-memory broadcast.  No cross-lane reduction; fixed k order.
+constexpr int SK_ROWS = 16, SK_KC = 128, SK_MPAD = 65;
+
+__global__ void __launch_bounds__(128) gemm_skinny_kernel(GemmParams p) {
+    __shared__ float xT[SK_KC][SK_MPAD];                 // [k][m], padded: conflict-free transposed stores
+    __shared__ __align__(16) float ws[SK_ROWS][SK_KC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.x * SK_ROWS;
+    float acc[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[h][r] = 0.f;
+
+    for (int k0 = 0; k0 < p.K; k0 += SK_KC) {
+        const int kc = min(SK_KC, p.K - k0);             // multiple of 4
+        for (int idx = tid; idx < 64 * (SK_KC / 4); idx += 128) {
+            const int m = idx / (SK_KC / 4), kq = (idx - m * (SK_KC / 4)) * 4;
+            float4 v = make_float4(0, 0, 0, 0);
+            if (m < p.M && kq < kc) v = __ldg(reinterpret_cast<const float4*>(p.A.row(m) + k0 + kq));
+            xT[kq + 0][m] = v.x; xT[kq + 1][m] = v.y; xT[kq + 2][m] = v.z; xT[kq + 3][m] = v.w;
+        }
+        for (int idx = tid; idx < SK_ROWS * (SK_KC / 4); idx += 128) {
+            const int r = idx / (SK_KC / 4), kq = (idx - r * (SK_KC / 4)) * 4;
+            float4 v = make_float4(0, 0, 0, 0);
+            if (n0 + r < p.N && kq < kc) v = __ldg(reinterpret_cast<const float4*>(p.W + (long long)(n0 + r) * p.ldw + k0 + kq));
+            *reinterpret_cast<float4*>(&ws[r][kq]) = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < SK_KC; kk += 4) {
+            float4 w4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) w4[r] = *reinterpret_cast<const float4*>(&ws[warp * 4 + r][kk]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float x0 = xT[kk + j][lane], x1 = xT[kk + j][lane + 32];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float wv = j == 0 ? w4[r].x : (j == 1 ? w4[r].y : (j == 2 ? w4[r].z : w4[r].w));
+                    acc[0][r] = fmaf(wv, x0, acc[0][r]);
+                    acc[1][r] = fmaf(wv, x1, acc[1][r]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int m = lane + 32 * h;
+        if (m >= p.M) continue;
+        float* crow = p.C.row(m);
+        const float* rrow = p.R.ptr ? p.R.row(m) : nullptr;
+        const float* grow = p.gate ? p.gate + (m / p.gate_rpb) * p.gate_ld : nullptr;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int n = n0 + warp * 4 + r;
+            if (n >= p.N) continue;
+            float v = acc[h][r];
+            if (p.bias) v += __ldg(p.bias + n);
+            v = apply_act(v, p.act) * p.alpha;
+            if (grow) v *= __ldg(grow + n);
+            if (rrow) v += rrow[n];
+            crow[n] = v;
+        }
+    }
+}
+
 }  // namespace
 
 int launch_gemm(const GemmParams& p, cudaStream_t stream) {
@@ -123,6 +195,12 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     MB_REQUIRE((reinterpret_cast<uintptr_t>(p.A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0,
                "GEMM operands must be 16-byte aligned");
     if (p.M <= 0 || p.N <= 0) return 0;
+    if (p.M <= 64) {
+        gemm_skinny_kernel<<<(p.N + SK_ROWS - 1) / SK_ROWS, 128, 0, stream>>>(p);
+        MB_LAUNCH_CHECK();
+        ++g_launch_count;
+        return 0;
+    }
     dim3 grid((p.N + BN - 1) / BN, (unsigned)((p.M + BM - 1) / BM));
     gemm_f32_kernel<<<grid, 256, 0, stream>>>(p);
     MB_LAUNCH_CHECK();

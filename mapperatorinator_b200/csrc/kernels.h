@@ -175,6 +175,9 @@ struct MegaParams {
     unsigned int* sync_counter;               // zeroed by the host before every launch
     int* error_flag;                          // 0 ok, 1 grid-barrier timeout, 2 weight-copy timeout
     int max_steps;
+    const int* row_slot;                      // encoder slot of each decoder row (read once per token)
+    unsigned long long* trace;                // optional [n_phases][6] globaltimer stamps of CTA 0 at token `trace_step`
+    int trace_step;
 };
 size_t mega_smem_bytes();
 int launch_megakernel(const MegaParams& mp, int grid, cudaStream_t stream);

@@ -76,9 +76,12 @@ class B200DiT:
         return iter([torch.empty(0, device=self.device)])
 
     def _mask(self, attn_mask):
-        key = None if attn_mask is None else (attn_mask.data_ptr(), tuple(attn_mask.shape))
-        if self._mask_cache[0] != key:
-            self._mask_cache = (key, _classify_mask(None if attn_mask is None else attn_mask.to(self.device)))
+        # cached by object identity (the cache holds the tensor, so the id cannot be recycled); the sampling loop passes the
+        # same mask object at every step
+        if attn_mask is None:
+            return "none", 0, None
+        if self._mask_cache[0] is not attn_mask:
+            self._mask_cache = (attn_mask, _classify_mask(attn_mask.to(self.device)))
         return self._mask_cache[1]
 
     def forward_with_cfg(self, x, t, c, y, cfg_scale, attn_mask=None, key_padding_mask=None):
@@ -192,6 +195,62 @@ class SpacedDiffusion:
             out = self.p_sample(model, img, t, clip_denoised, denoised_fn, cond_fn, mk, None if step_noise is None else step_noise[k])
             img = out["sample"]
         return img
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000) -> torch.Tensor:
+    """osu_diffusion/utils/positional_embedding.py:29-49 (cat[cos, sin]); host-side context preparation."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def build_context(seq_o: torch.Tensor, seq_d: torch.Tensor, type_index: torch.Tensor, n_types: int = 16) -> torch.Tensor:
+    """The tensor part of `DiffisionPipeline.events_to_sequence` (diffusion_pipeline.py:380-387): per point
+    [timestep_embedding(o * 0.1, 128) | timestep_embedding(d, 128) | one-hot type] -> seq_c (272, T)."""
+    onehot = torch.nn.functional.one_hot(type_index.long(), n_types).float()
+    return torch.cat([timestep_embedding(seq_o * 0.1, 128), timestep_embedding(seq_d, 128), onehot], dim=-1).T.contiguous()
+
+
+def band_attention_mask(seq_len: int, width: int, device=None) -> torch.Tensor:
+    """diffusion_pipeline.py:146-148 without the Python loop: True = blocked; column i open for rows [i - w, i + w)."""
+    r = torch.arange(seq_len, device=device)[:, None]
+    c = torch.arange(seq_len, device=device)[None, :]
+    return ~((r >= c - width) & (r < c + width))
+
+
+def sample_sequence(dit: "B200DiT", seq_x: torch.Tensor, seq_c: torch.Tensor, y: torch.Tensor, y_null: torch.Tensor,
+                    cfg_scale: float = 1.0, timesteps=(100, 0, 0, 0, 0, 0, 0, 0, 0, 0), diffusion_steps: int = 1000,
+                    noise_schedule: str = "squaredcos_cap_v2", train_seq_len: int = 128, max_seq_len: int = 1024,
+                    overlap_buffer: int = 128, step_noise: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+    """The slider-free body of `DiffisionPipeline.generate` (diffusion_pipeline.py:139-287): CFG batch, band mask, chunks of
+    `max_seq_len` with `overlap_buffer` frozen / re-noised margins, in-paint mask, 100-step refinement of every chunk on
+    the device, then `to_positions` (x (512, 384)).  seq_x (2, T) in [-1, 1], seq_c (272, T), y / y_null (C,).
+    `step_noise[k]` optionally injects chunk k's noise tensor (steps, 2, 2, T_k) for parity runs.  Returns (2, T) osu! pixels."""
+    dev = dit.device
+    T = seq_x.shape[1]
+    diffusion = create_diffusion(list(timesteps), noise_schedule, diffusion_steps)
+    attn_mask = band_attention_mask(T, train_seq_len, dev)
+    z = torch.cat([seq_x[None], seq_x[None]], 0).to(dev).float()
+    c = torch.cat([seq_c[None], seq_c[None]], 0).to(dev).float()
+    yy = torch.stack([y, y_null], 0).to(dev).float()
+    full = z.clone()
+    k = 0
+    for i in range(0, T - overlap_buffer * 2, max_seq_len - overlap_buffer * 2):
+        end = min(i + max_seq_len, T)
+        if i > 0:   # second buffer is regenerated from the start state (:281)
+            full[:, :, i + overlap_buffer:i + overlap_buffer * 2] = z[:, :, i + overlap_buffer:i + overlap_buffer * 2]
+        z_part = full[:, :, i:end].contiguous()
+        mask = torch.zeros_like(z_part, dtype=torch.bool)
+        mask[:, :, (overlap_buffer if i > 0 else 0):] = True
+        mk = dict(c=c[:, :, i:end].contiguous(), y=yy, cfg_scale=cfg_scale, attn_mask=attn_mask[i:end, i:end].contiguous(),
+                  key_padding_mask=None)
+        out = diffusion.p_sample_loop(dit.forward_with_cfg, z_part.shape, z_part, denoised_fn=InpaintDenoiser(mask, z_part),
+                                      clip_denoised=True, model_kwargs=mk, step_noise=None if step_noise is None else step_noise[k])
+        full[:, :, i:end] = out
+        k += 1
+    pos = (full[:1] + 1) / 2 * torch.tensor((512.0, 384.0), device=dev)[None, :, None]
+    return pos[0]
 
 
 def create_diffusion(timestep_respacing, noise_schedule: str = "linear", diffusion_steps: int = 1000, **kw) -> SpacedDiffusion:

@@ -96,3 +96,18 @@ def dit_case(dc, T: int = 200, seed: int = 4):
     ip = torch.ones_like(x, dtype=torch.bool)
     ip[:, :, :40] = False
     return x, c, y, noise, ip, band_mask(T, 128)
+
+
+def dit_chunk_case(dc, T: int = 300, seed: int = 8):
+    """Chunked refinement case: band 32, max_seq_len 128, overlap 16 -> 3 chunks with frozen / re-noised margins."""
+    g = torch.Generator().manual_seed(seed)
+    seq_x = torch.rand(2, T, generator=g) * 2 - 1
+    seq_c = torch.randn(dc.context_size, T, generator=g)
+    y = (torch.rand(dc.class_size, generator=g) < 0.1).float()
+    y_null = (torch.rand(dc.class_size, generator=g) < 0.05).float()
+    return seq_x, seq_c, y, y_null, dict(train_seq_len=32, max_seq_len=128, overlap_buffer=16)
+
+
+def dit_chunk_noise(k: int, shape, steps: int = 100) -> torch.Tensor:
+    g = torch.Generator().manual_seed(1000 + k)
+    return torch.randn(steps, *shape, generator=g)

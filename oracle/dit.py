@@ -184,3 +184,29 @@ def p_sample_loop(w: W, cfg, sched: Schedule, z: torch.Tensor, c, y, cfg_scale: 
         if return_trace:
             trace.append(img.clone())
     return (img, trace) if return_trace else img
+
+
+def sample_sequence(w: W, cfg, seq_x, seq_c, y, y_null, cfg_scale: float = 1.0, train_seq_len: int = 128, max_seq_len: int = 1024,
+                    overlap_buffer: int = 128, chunk_noise=None, sched: Optional[Schedule] = None):
+    """Slider-free `DiffisionPipeline.generate` (diffusion_pipeline.py:139-287): CFG pair, band mask, overlapping chunks,
+    in-paint mask, `to_positions`.  `chunk_noise(k, shape)` supplies chunk k's (steps, *shape) noise.  Returns (2, T)."""
+    sched = sched or Schedule()
+    T = seq_x.shape[1]
+    am = band_mask(T, train_seq_len)
+    z = torch.cat([seq_x[None], seq_x[None]], 0)
+    c = torch.cat([seq_c[None], seq_c[None]], 0)
+    yy = torch.stack([y, y_null], 0)
+    full = z.clone()
+    k = 0
+    for i in range(0, T - overlap_buffer * 2, max_seq_len - overlap_buffer * 2):
+        end = min(i + max_seq_len, T)
+        if i > 0:
+            full[:, :, i + overlap_buffer:i + overlap_buffer * 2] = z[:, :, i + overlap_buffer:i + overlap_buffer * 2]
+        z_part = full[:, :, i:end].clone()
+        mask = torch.zeros_like(z_part, dtype=torch.bool)
+        mask[:, :, (overlap_buffer if i > 0 else 0):] = True
+        noise = chunk_noise(k, z_part.shape)
+        full[:, :, i:end] = p_sample_loop(w, cfg, sched, z_part, c[:, :, i:end], yy, cfg_scale, am[i:end, i:end], noise, inpaint_mask=mask)
+        k += 1
+    pos = (full[:1] + 1) / 2 * torch.tensor((512.0, 384.0))[None, :, None]
+    return pos[0]

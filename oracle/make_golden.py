@@ -111,6 +111,38 @@ def main():
                                                       device="cpu").numpy()
     finally:
         torch.randn_like = orig
+    # the chunk loop / in-paint mask / to_positions of the reference's own DiffisionPipeline.generate (diffusion_pipeline.py:111-287):
+    # only the event<->tensor conversions are stubbed (they need slider + real beatmaps)
+    import types as _types
+    import diffusion_pipeline as dp
+    seq_x, seq_c, yv, y_null, geo = cases.dit_chunk_case(dc)
+    pipe = object.__new__(dp.DiffisionPipeline)
+    pipe.device = "cpu"; pipe.model = m; pipe.tokenizer = None; pipe.refine_model = None
+    pipe.diffusion_steps = 1000; pipe.noise_schedule = "squaredcos_cap_v2"; pipe.seq_len = geo["train_seq_len"]
+    pipe.max_seq_len = geo["max_seq_len"]; pipe.overlap_buffer = geo["overlap_buffer"]; pipe.timesteps = [100, 0, 0, 0, 0, 0, 0, 0, 0, 0]
+    pipe.cfg_scale = 1.0; pipe.refine_iters = 0; pipe.random_init = False; pipe.types_first = True; pipe.pad_sequence = False
+    pipe.start_time = None; pipe.end_time = None; pipe.has_sv = True
+    Tn = seq_x.shape[1]
+    pipe.events_to_sequence = lambda events, timing, sm: (seq_x.clone(), torch.arange(Tn).float(), seq_c.clone(), Tn, {}, [])
+    vecs = iter([yv.clone(), y_null.clone()])
+    pipe.get_class_vector = lambda cfg_: next(vecs)
+    captured = {}
+    pipe.events_with_pos = lambda events, positions, idx: captured.setdefault("pos", positions.clone())
+    state = {"k": -1, "it": None}
+    def _randn_like(a):
+        if state["it"] is None or state["left"] == 0:
+            state["k"] += 1
+            state["it"] = iter(cases.dit_chunk_noise(state["k"], a.shape)); state["left"] = 100
+        state["left"] -= 1
+        return next(state["it"])
+    orig2 = torch.randn_like
+    torch.randn_like = _randn_like
+    try:
+        gc = _types.SimpleNamespace(difficulty=None, descriptors=None, negative_descriptors=None, circle_size=None, slider_multiplier=1.4)
+        pipe.generate([], gc, [], verbose=False)
+    finally:
+        torch.randn_like = orig2
+    dit_out["chunked_positions"] = captured["pos"].numpy()
     dit_out["timestep_map"] = np.array(diff.timestep_map)
     dit_out["schedule"] = np.stack([diff.sqrt_recip_alphas_cumprod, diff.sqrt_recipm1_alphas_cumprod, diff.posterior_log_variance_clipped,
                                     np.log(diff.betas), diff.posterior_mean_coef1, diff.posterior_mean_coef2], 1)

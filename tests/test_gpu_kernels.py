@@ -13,7 +13,8 @@ def _g(seed):
     return torch.Generator().manual_seed(seed)
 
 
-@pytest.mark.parametrize("M,N,K", [(1, 4, 128), (77, 130, 388), (300, 768, 768), (257, 3667, 128), (513, 256, 600)])
+@pytest.mark.parametrize("M,N,K", [(1, 4, 128), (77, 130, 388), (300, 768, 768), (257, 3667, 128), (513, 256, 600),
+                                   (50, 768, 768), (64, 3667, 128), (33, 130, 388), (18, 768, 3072)])   # M <= 64: skinny kernel
 @pytest.mark.parametrize("act", ["none", "gelu", "gelu_tanh", "silu"])
 def test_gemm_epilogues(M, N, K, act):
     from mapperatorinator_b200 import ops

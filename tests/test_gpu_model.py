@@ -165,3 +165,19 @@ def test_dit_sample_loop_both_seams(tiny_dit):
     loop = diff.p_sample_loop(dit.forward_with_cfg, x.shape, x.cuda(), denoised_fn=closure, clip_denoised=True, model_kwargs=mk,
                               step_noise=noise.cuda()).cpu()
     assert (loop - ref).abs().max() <= 1e-3
+
+
+def test_dit_chunked_sample_sequence(tiny_dit):
+    """`diffusion.sample_sequence` (the slider-free body of DiffisionPipeline.generate, fused loop per chunk) vs the reference
+    pipeline's own output: 1e-3 in normalised coordinates = 0.256 px in x."""
+    from mapperatorinator_b200.diffusion import sample_sequence
+    gold = np.load(os.path.join(GOLDEN, "dit_reference.npz"))
+    dc, sd, dit = tiny_dit
+    seq_x, seq_c, y, y_null, geo = cases.dit_chunk_case(dc)
+    shapes = []
+    T, ob, ms = seq_x.shape[1], geo["overlap_buffer"], geo["max_seq_len"]
+    for i in range(0, T - ob * 2, ms - ob * 2):
+        shapes.append((2, 2, min(i + ms, T) - i))
+    noise = [cases.dit_chunk_noise(k, s).cuda() for k, s in enumerate(shapes)]
+    pos = sample_sequence(dit, seq_x, seq_c, y, y_null, 1.0, step_noise=noise, **geo).cpu().numpy()
+    assert np.abs(pos - gold["chunked_positions"]).max() <= 0.256

@@ -81,3 +81,15 @@ def test_dit_forward_and_loop():
     assert np.allclose(mine, gold["schedule"], rtol=1e-12, atol=0)
     res = dit_oracle.p_sample_loop(sd, dc, sched, x, c, y, 1.0, am, noise, inpaint_mask=ip).numpy()
     assert np.abs(res - gold["p_sample_loop"]).max() <= 2e-5
+
+
+def test_dit_chunked_pipeline_loop():
+    """Oracle chunk loop vs the reference's own `DiffisionPipeline.generate` (chunks with frozen / re-noised overlap, in-paint
+    mask, to_positions)."""
+    gold = np.load(os.path.join(GOLDEN, "dit_reference.npz"))
+    dc = tiny_dit_config()
+    sd = init_dit_state_dict(dc, 1)
+    seq_x, seq_c, y, y_null, geo = cases.dit_chunk_case(dc)
+    pos = dit_oracle.sample_sequence(sd, dc, seq_x, seq_c, y, y_null, 1.0, chunk_noise=cases.dit_chunk_noise, **geo).numpy()
+    assert pos.shape == gold["chunked_positions"].shape
+    assert np.abs(pos - gold["chunked_positions"]).max() <= 2e-3          # pixels (coordinates are scaled by 512 / 384)

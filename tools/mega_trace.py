@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Per-phase timeline of the persistent decode megakernel (CTA 0, 9th token) at v29 dimensions: where does a token's time go?"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from mapperatorinator_b200 import TokenLayout, _lib, v29_model_config  # noqa: E402
+from mapperatorinator_b200.modeling import B200Mapperatorinator  # noqa: E402
+from mapperatorinator_b200.weights import init_model_state_dict  # noqa: E402
+
+cfg = v29_model_config()
+layout = TokenLayout.from_json(os.path.join(ROOT, "tests", "golden", "tokenizer_v29.json"))
+model = B200Mapperatorinator(cfg, init_model_state_dict(cfg, 0), max_windows=2, max_batch=2)
+windows, _, _ = bench.segment(bench.synth_song(0, 20.0), cfg)
+model.engine.encode(windows[:2].cuda(), 0)
+model.engine.set_option("mega_trace", 1)
+prompt = torch.tensor([bench.prompt_for(0, [])])
+for _ in range(3):
+    model.engine.generate([0], prompt, prompt.ne(0), layout, bench.gen_kwargs(0, 211, prompt.shape[1]))
+n = 12 * 8 + 2
+out = np.zeros((n, 6), dtype=np.uint64)
+_lib.check(_lib.load().mb200_model_read_trace(model.engine.handle, out.ctypes.data, n))
+t = out.astype(np.int64)
+names = ["qkv", "self_attn", "out", "q_c", "cross_attn", "out_c", "fc1", "fc2"]
+tot = t[-1, 5] - t[0, 0]
+print(f"token total {tot / 1e3:.1f} us over {n} phases")
+print("phase            own_stage  sync   pref+wait   math   barrier    total (us)")
+agg = {}
+for i in range(n):
+    nm = names[i % 8] if i < 96 else ("proj_out" if i == 96 else "sample")
+    s0, s1, s2, s3, s4, s5 = (t[i, j] for j in range(6))
+    if nm in ("self_attn", "cross_attn", "sample"):
+        seg = (0, 0, 0, s4 - s0, s5 - s4)
+    else:
+        seg = (s1 - s0, s2 - s1, s3 - s2, s4 - s3, s5 - s4)
+    agg.setdefault(nm, []).append(seg + (s5 - s0,))
+for nm, v in agg.items():
+    a = np.array(v, dtype=np.float64).mean(0) / 1e3
+    print(f"{nm:12s} x{len(v):3d} {a[0]:8.2f} {a[1]:8.2f} {a[2]:8.2f} {a[3]:7.2f} {a[4]:9.2f} {a[5]:8.2f}")
