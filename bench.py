@@ -159,6 +159,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("MB200_PDL", "0")))
     ap.add_argument("--windows", type=int, default=0, help="debug: truncate the song to this many windows")
+    ap.add_argument("--tc", type=int, default=int(os.environ.get("MB200_TC", "1")), help="1 = tcgen05 3xTF32 GEMMs where eligible, 0 = fp32 SIMT GEMM everywhere")
     ap.add_argument("--mega", type=int, default=1, help="1 = persistent token-loop megakernel (default), 0 = CUDA-graph replay per token")
     ap.add_argument("--cpu-threads", type=int, default=int(os.environ.get("MB200_CPU_THREADS", "0")),
                     help="torch threads of the CPU arm (0 = min(cores, 32): more threads only slow a batch-1 decoder down)")
@@ -193,6 +194,7 @@ def main() -> None:
     pinned = windows.pin_memory()
     resident = windows.to(dev)
     lib = _lib.load()
+    lib.mb200_set_tensor_cores(int(args.tc))
 
     def step_resident():
         song.encode_song(resident)
@@ -220,6 +222,8 @@ def main() -> None:
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.mb200_launch_count()
+        mstats = np.zeros(3, dtype=np.float64)
+        lib.mb200_model_mega_stats(model.engine.handle, mstats.ctypes.data, 1)      # reset the megakernel event counters
         e0.record()
         toks = 0
         for _ in range(steps):
@@ -231,6 +235,8 @@ def main() -> None:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         launches = lib.mb200_launch_count() - l0
+        lib.mb200_model_mega_stats(model.engine.handle, mstats.ctypes.data, 0)
+        timed.mega = mstats.copy()
         if world > 1:
             tt = torch.tensor([ms, float(toks)], device=dev, dtype=torch.float64)
             mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -241,15 +247,13 @@ def main() -> None:
     with ClockSampler(local) as clk:
         ms, toks, launches, streams = timed(step_resident, args.steps, args.warmup)
     clocks = clk.summary()
+    mega_resident, ms_resident = timed.mega, ms
     ms_e2e, toks_e2e, _, streams2 = timed(step_e2e, max(1, args.steps // 2), 1)
     assert streams == streams2, "resident-encoder path and per-window drop-in path must emit identical tokens"
 
-    # ---- roofline of the dominant kernel (gemv_kernel: every decoder projection + proj_out), measured live with events ----
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream --------------------------------
     d, f, V, L = cfg.d_model, cfg.ffn_dim, cfg.vocab_size_out, cfg.decoder_layers
-    out_us = (np.zeros(4, dtype=np.float32))
-    _lib.check(lib.mb200_model_profile_step(model.engine.handle, 1, 1, 50 + NEW_TOKENS, 20, out_us.ctypes.data, torch.cuda.current_stream().cuda_stream))
-    n_gemv = int(out_us[3]) // 1000000
-    w_bytes = 4 * (L * (3 * d * d + 2 * d * d + d * d + 2 * d * f) + V * d)                  # weights streamed once per token
+    w_bytes = 4 * (L * (3 * d * d + 2 * d * d + d * d + 2 * d * f) + V * d)                  # decoder weights streamed once per token
     ctx = 50 + NEW_TOKENS // 2
     kv_bytes = 4 * L * 2 * (cfg.max_source_positions + ctx) * d                               # cross + self K/V read per token
     peaks = {}
@@ -258,14 +262,30 @@ def main() -> None:
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    gemv_us = float(out_us[0])
-    achieved = (w_bytes / n_gemv) / (gemv_us / n_gemv * 1e-6) / 1e9 if gemv_us > 0 else None
-    roofline = {"bound": "hbm", "kernel": f"gemv_kernel<1> ({n_gemv} launches per token: decoder q|k|v, out, cross-q, cross-out, fc1, fc2 x{L} + proj_out)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "bytes_per_launch": w_bytes / n_gemv, "us_per_launch": gemv_us / n_gemv,
-                "per_token_us": {"gemv": gemv_us, "attention": float(out_us[1]), "sample": float(out_us[2])},
-                "decode_step_bytes": w_bytes + kv_bytes, "decode_step_floor_us": (w_bytes + kv_bytes) / (peak * 1e3)}
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    mega = mega_resident
+    if args.mega and mega[0] > 0:
+        # persistent token-loop kernel: one launch per window decodes NEW_TOKENS-1 tokens; events recorded around every launch
+        tok_per_launch = mega[2] / mega[0]
+        us_per_launch = 1000.0 * mega[1] / mega[0]
+        bytes_per_launch = (w_bytes + kv_bytes) * tok_per_launch
+        achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9
+        roofline = {"bound": "hbm", "kernel": "decode_megakernel<1> (persistent cooperative kernel: all layers of all tokens of one generate() call)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": bytes_per_launch, "us_per_launch": us_per_launch, "tokens_per_launch": tok_per_launch,
+                    "us_per_token": us_per_launch / tok_per_launch, "bytes_per_token": w_bytes + kv_bytes,
+                    "share_of_step": mega[1] / (ms_resident), "token_floor_us": (w_bytes + kv_bytes) / (peak * 1e3)}
+    else:
+        out_us = np.zeros(4, dtype=np.float32)
+        _lib.check(lib.mb200_model_profile_step(model.engine.handle, 1, 1, 50 + NEW_TOKENS, 20, out_us.ctypes.data, torch.cuda.current_stream().cuda_stream))
+        n_gemv = int(out_us[3]) // 1000000
+        gemv_us = float(out_us[0])
+        achieved = (w_bytes / n_gemv) / (gemv_us / n_gemv * 1e-6) / 1e9 if gemv_us > 0 else None
+        roofline = {"bound": "hbm", "kernel": f"gemv_kernel<1> ({n_gemv} launches per token, CUDA-graph path; eager event timing includes launch gaps)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+                    "peak_source": peak_src, "bytes_per_launch": w_bytes / n_gemv, "us_per_launch": gemv_us / n_gemv,
+                    "per_token_us": {"gemv": gemv_us, "attention": float(out_us[1]), "sample": float(out_us[2])},
+                    "token_floor_us": (w_bytes + kv_bytes) / (peak * 1e3)}
 
     if rank != 0:
         if world > 1:
@@ -299,7 +319,8 @@ def main() -> None:
         "dtype": "f32", "data": "synthetic", "config": workload_config(n_windows), "clocks": clocks,
         "e2e": {"value": toks_e2e / (ms_e2e / 1000), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "server.model_generate per window (host tensors in, CPU LongTensor out)"},
-        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "pdl": bool(args.pdl)}))
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "pdl": bool(args.pdl), "tensor_cores": bool(args.tc),
+        "token_stream_sha1": __import__("hashlib").sha1(json.dumps(streams).encode()).hexdigest()}))
     if world > 1:
         dist.destroy_process_group()
 

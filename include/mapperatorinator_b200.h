@@ -165,6 +165,9 @@ int mb200_model_profile_step(mb200_model* m, int32_t rows, int32_t batch, int32_
  * %globaltimer stamps of CTA 0 for every micro-phase of the 9th token); read them back as out[n_phases][6] nanoseconds:
  * {phase start, activations staged, weights landed, (unused), math done, grid barrier passed}. */
 int mb200_model_read_trace(mb200_model* m, uint64_t* out, int32_t n_phases);
+/* CUDA-event totals of the persistent token-loop kernel (recorded on the launching stream around every launch):
+ * out[0] = launches, out[1] = device milliseconds, out[2] = tokens decoded inside them; reset != 0 clears the counters. */
+int mb200_model_mega_stats(mb200_model* m, double* out, int32_t reset);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Kernel-level entry points (parity tests of the individual kernels; not needed by an integrator).
@@ -172,6 +175,11 @@ int mb200_model_read_trace(mb200_model* m, uint64_t* out, int32_t n_phases);
 int mb200_op_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, const float* bias, int32_t act,
                   float alpha, const float* residual, int64_t ldr, const float* gate, int64_t gate_ld, int32_t gate_rpb, int32_t M,
                   int32_t N, int32_t K, void* cuda_stream);
+/* the tcgen05 3xTF32 GEMM on its own (registers W's lo mirror, runs, synchronises, checks the pipeline error flag) */
+int mb200_op_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, const float* bias, int32_t act,
+                     float alpha, const float* residual, int64_t ldr, int32_t M, int32_t N, int32_t K, void* cuda_stream);
+/* 0 = route every GEMM through the fp32 SIMT kernel (A/B comparisons), 1 = tensor cores where eligible (default) */
+int mb200_set_tensor_cores(int32_t enabled);
 int mb200_op_layernorm(const float* x, float* y, const float* w, const float* b, const float* shift, const float* scale,
                        int32_t rows_per_batch, int32_t rows, int32_t dim, float eps, void* cuda_stream);
 int mb200_op_attention(const float* q, const float* k, const float* v, float* o, int32_t B, int32_t H, int32_t Tq, int32_t Tk,

@@ -56,6 +56,27 @@ extern "C" int mb200_op_gemm(const float* A, int64_t lda, const float* W, int64_
     return launch_gemm(g, (cudaStream_t)stream);
 }
 
+extern "C" int mb200_op_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, const float* bias, int32_t act,
+                                float alpha, const float* residual, int64_t ldr, int32_t M, int32_t N, int32_t K, void* stream) {
+    GemmParams g{};
+    g.A = plain_map(A, lda); g.W = W; g.ldw = ldw; g.C = plain_map(C, ldc); g.bias = bias; g.act = act; g.alpha = alpha;
+    g.gate = nullptr; g.gate_ld = 0; g.gate_rpb = 1;
+    g.R = residual ? plain_map(residual, ldr) : RowMap{nullptr, 0, 0, 0};
+    g.M = M; g.N = N; g.K = K;
+    int s = tc_register_weight(W, (long long)N * ldw);
+    if (s) return s;
+    MB_REQUIRE(tc_gemm_eligible(g), "problem not eligible for the tcgen05 path (M >= 512, K % 4 == 0, 16-byte aligned operands)");
+    s = launch_gemm_tc(g, (cudaStream_t)stream);
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    tc_unregister_weight(W);      // W belongs to the caller (a torch tensor whose address may be recycled)
+    if (s) return s;
+    MB_CUDA_CHECK(e);
+    MB_REQUIRE(tc_gemm_error() == 0, "tcgen05 GEMM pipeline wait timed out");
+    return 0;
+}
+
+extern "C" int mb200_set_tensor_cores(int32_t enabled) { g_tc_enabled = enabled; return 0; }
+
 extern "C" int mb200_op_layernorm(const float* x, float* y, const float* w, const float* b, const float* shift, const float* scale,
                                   int32_t rows_per_batch, int32_t rows, int32_t dim, float eps, void* stream) {
     LayerNormParams p{};

@@ -56,9 +56,18 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// The 464 MB of decoder weights stream through the 126 MB L2 once per token.  With the default policy they evict everything
+// else — LayerNorm affine vectors, biases, phase descriptors, the K/V caches — so every small latency-critical load of the next
+// token misses to DRAM.  Tagging the weight stream evict-first keeps that small hot set resident in L2.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    const unsigned long long pol = l2_evict_first_policy();
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
 // rows [r0, r1) of an N-row GEMV owned by CTA `cta` of `G`
@@ -69,13 +78,14 @@ __device__ __forceinline__ void cta_rows(int N, int cta, int G, int& r0, int& r1
 }
 
 // thread 0: start streaming this CTA's weight rows of GEMV phase `ph` into wbuf[buf]
-__device__ __forceinline__ void prefetch_weights(const MegaPhase* ph, float* dst, unsigned long long* bar, int cta, int G) {
+__device__ __forceinline__ void prefetch_weights(const float* W, long long ldw, int N, int K, float* dst, unsigned long long* bar, int cta,
+                                                 int G) {
     int r0, r1;
-    cta_rows(ph->g.N, cta, G, r0, r1);
-    const unsigned bytes = (unsigned)(r1 - r0) * (unsigned)ph->g.K * 4u;
+    cta_rows(N, cta, G, r0, r1);
+    const unsigned bytes = (unsigned)(r1 - r0) * (unsigned)K * 4u;
     if (bytes == 0) { mbar_arrive(bar); return; }
     mbar_arrive_expect_tx(bar, bytes);
-    bulk_g2s(dst, ph->g.W + (long long)r0 * ph->g.ldw, bytes, bar);
+    bulk_g2s(dst, W + (long long)r0 * ldw, bytes, bar);
 }
 
 __device__ __forceinline__ bool wait_weights(unsigned long long* bar, unsigned parity, int* error_flag) {
@@ -131,7 +141,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
     __syncthreads();
     unsigned int g_idx = 0;          // running index of GEMV phases (selects buffer + mbarrier parity)
     unsigned int sync_target = 0;
-    if (tid == 0) prefetch_weights(&mp.phases[mp.first_gemv], sm.wbuf[0], &sm.mbar[0], cta, G);
+    if (tid == 0) {
+        const MegaPhase* f = &mp.phases[mp.first_gemv];
+        prefetch_weights(f->g.W, f->g.ldw, f->g.N, f->g.K, sm.wbuf[0], &sm.mbar[0], cta, G);
+    }
 
     // phase descriptors are double-buffered in shared memory: slot `cur` is the phase being executed, slot `cur ^ 1` is
     // filled with the NEXT phase's descriptor while this one runs (its latency never sits on the critical path)
@@ -183,7 +196,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                 // The next GEMV's weight slice is requested only now: measured on B200, issuing the ~5-9 MB bulk stream at
                 // the top of the phase queued this phase's few small latency-critical loads (activations, LN affine, bias)
                 // behind it and cost ~2.5 us per phase.  It still has the rest of this phase plus the next prologue to land.
-                if (tid == 0) prefetch_weights(&mp.phases[ph.next_gemv], sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, G);
+                // issued by the LAST warp (it owns the fewest rows), from fields already in shared memory
+                if (tid == MEGA_THREADS - 32) prefetch_weights(ph.nx_W, ph.nx_ldw, ph.nx_N, ph.nx_K, sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, G);
                 wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, mp.error_flag);   // on a timeout the error flag ends the loop at the next token
                 MEGA_TRACE(3);
                 {

@@ -126,6 +126,7 @@ struct mb200_dit {
     const float *pos_freqs = nullptr, *t_freqs = nullptr;
     DevBufD a0, x, h, qkv, att, ffn, o4, temb, te1, te, ye1, ye, bcond, mods, fmod, tvals, state0, state1;
     int mod_steps = 0;
+    std::vector<const float*> tc_weights;
 };
 
 extern "C" int mb200_dit_create(mb200_dit** out, const mb200_dit_config* cfg) {
@@ -140,7 +141,11 @@ extern "C" int mb200_dit_create(mb200_dit** out, const mb200_dit_config* cfg) {
     return 0;
 }
 
-extern "C" void mb200_dit_destroy(mb200_dit* d) { delete d; }
+extern "C" void mb200_dit_destroy(mb200_dit* d) {
+    if (!d) return;
+    for (const float* w : d->tc_weights) tc_unregister_weight(w);
+    delete d;
+}
 
 extern "C" int mb200_dit_set_weight(mb200_dit* d, const char* name, const float* data, int64_t numel) {
     MB_REQUIRE(d && name && data && !d->finalized, "bad argument / state");
@@ -164,7 +169,7 @@ extern "C" int mb200_dit_finalize(mb200_dit* dd) {
             names.push_back(p + s);
     }
     std::vector<float> pack;
-    std::unordered_map<std::string, size_t> offs;
+    std::unordered_map<std::string, size_t> offs, sizes;
     for (const auto& n : names) {
         MB_REQUIRE(dd->host_w.count(n) == 1, "missing DiT weight " + n);
         std::vector<float> v = dd->host_w.at(n);
@@ -174,7 +179,7 @@ extern "C" int mb200_dit_finalize(mb200_dit* dd) {
         size_t off = (pack.size() + 63) & ~size_t(63);
         pack.resize(off + v.size());
         std::copy(v.begin(), v.end(), pack.begin() + off);
-        offs[n] = off;
+        offs[n] = off; sizes[n] = v.size();
     }
     // sinusoid frequency tables, same fp32 chain as positional_embedding.timestep_embedding (:40-46)
     auto freqs = [&](int dim) {
@@ -193,6 +198,13 @@ extern "C" int mb200_dit_finalize(mb200_dit* dd) {
     MB_TRY(dd->arena.ensure(pack.size() * 4));
     MB_CUDA_CHECK(cudaMemcpy(dd->arena.p, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice));
     for (auto& kv : offs) dd->w[kv.first] = dd->arena.f() + kv.second;
+    // tf32 "lo" mirrors for the tensor-core GEMMs (every 2-D weight of the blocks and the embedders)
+    for (const auto& n : names)
+        if (n.find("weight") != std::string::npos && sizes.at(n) >= (size_t)64 * 32) {
+            dd->tc_weights.push_back(dd->w[n]);
+            MB_TRY(tc_register_weight(dd->w[n], (long long)sizes.at(n)));
+        }
+    MB_CUDA_CHECK(cudaDeviceSynchronize());
     dd->pos_freqs = dd->w["__pos_freqs"]; dd->t_freqs = dd->w["__t_freqs"];
     MB_REQUIRE(dd->host_w.at("context_embedder.mlp.0.weight").size() == (size_t)d * (c.in_channels * c.pos_freq_dim + c.context_size),
                "context_embedder shape mismatch");

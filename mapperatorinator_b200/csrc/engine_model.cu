@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -67,12 +68,17 @@ struct mb200_model {
     std::map<std::pair<int, int>, long long> graph_nodes;   // (rows, n_splits_self) -> token-step graph
     bool use_pdl = false;
     cudaStream_t cap_stream = nullptr;
+    std::map<std::tuple<int, int, int>, int> prefill_seen;                                   // (rows, P, position rule)
+    std::map<std::tuple<int, int, int>, std::pair<cudaGraphExec_t, long long>> prefill_graphs;   // -> graph + node count
     // persistent megakernel path
     bool use_mega = true;
     int num_sms = 0;
     DevBuf g_megasync;                  // [0] grid-barrier counter, [8] error flag
     DevBuf mega_trace;                  // optional per-phase globaltimer stamps (option "mega_trace")
+    cudaEvent_t mega_ev[2] = {nullptr, nullptr};
+    double mega_ms = 0.0; long long mega_launches = 0, mega_tokens = 0;   // CUDA-event time of every megakernel launch
     std::map<std::pair<int, int>, std::pair<DevBuf*, int>> mega_phases;   // (rows, n_splits_self) -> device phase table
+    std::vector<const float*> tc_weights;  // weights with a registered tf32 lo mirror (unregistered in destroy)
 
     int d() const { return cfg.d_model; }
     int Ts() const { return cfg.src_seq_len / 2; }
@@ -157,6 +163,9 @@ extern "C" int mb200_model_create(mb200_model** out, const mb200_model_config* c
 extern "C" void mb200_model_destroy(mb200_model* m) {
     if (!m) return;
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+    for (auto& g : m->prefill_graphs) cudaGraphExecDestroy(g.second.first);
+    for (const float* w : m->tc_weights) tc_unregister_weight(w);
+    for (auto& kv : m->mega_phases) delete kv.second.first;
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     mel_plan_destroy(m->mel);
     if (m->h_flag) cudaFreeHost(m->h_flag);
@@ -266,6 +275,19 @@ extern "C" int mb200_model_finalize(mb200_model* m) {
     for (auto& o : eo) m->enc.push_back(fill(o, false));
     for (auto& o : dof) m->dec.push_back(fill(o, true));
     m->host_w.clear();
+    // tf32 "lo" mirrors of the weights that feed large (tensor-core) GEMMs: encoder stem + layers, cross K|V projections
+    {
+        const long long dd = (long long)d * d;
+        auto reg = [&](const float* w, long long n) -> int { m->tc_weights.push_back(w); return tc_register_weight(w, n); };
+        MB_TRY(reg(m->emb_w, (long long)d * c.mel.n_mels));
+        MB_TRY(reg(m->conv1_w, 3 * dd)); MB_TRY(reg(m->conv2_w, 3 * dd));
+        for (const auto& l : m->enc) {
+            MB_TRY(reg(l.wqkv, 3 * dd)); MB_TRY(reg(l.wo, dd));
+            MB_TRY(reg(l.fc1_w, (long long)f * d)); MB_TRY(reg(l.fc2_w, (long long)f * d));
+        }
+        for (const auto& l : m->dec) MB_TRY(reg(l.wkv_c, 2 * dd));
+        MB_CUDA_CHECK(cudaDeviceSynchronize());
+    }
 
     // ---- resident state ----
     m->max_rows = std::max(1, c.max_batch);
@@ -286,6 +308,11 @@ extern "C" int mb200_model_finalize(mb200_model* m) {
     MB_TRY(m->d_q.ensure((size_t)m->max_rows * d * sizeof(float)));
     MB_TRY(m->d_h.ensure((size_t)m->max_rows * f * sizeof(float)));
     MB_TRY(m->d_logits.ensure((size_t)m->max_rows * c.vocab_size_out * sizeof(float)));
+    {   // prefill activations for the largest possible call, so captured prefill graphs never see a reallocation
+        const size_t RPmax = (size_t)m->max_rows * c.tgt_seq_len;
+        MB_TRY(m->p_x.ensure(RPmax * d * 4)); MB_TRY(m->p_h.ensure(RPmax * d * 4)); MB_TRY(m->p_q.ensure(RPmax * d * 4));
+        MB_TRY(m->p_attn.ensure(RPmax * d * 4)); MB_TRY(m->p_ffn.ensure(RPmax * f * 4));
+    }
     {   // split-KV partials sized for the longest possible context so captured graphs never see a reallocation
         const int max_splits = std::max((c.tgt_seq_len + 63) / 64, (c.src_seq_len / 2 + 63) / 64);
         MB_TRY(m->d_parto.ensure((size_t)m->max_rows * c.heads * max_splits * 64 * sizeof(float)));
@@ -584,6 +611,8 @@ static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaSt
             int j = (i + 1) % n;
             while ((*collect)[j].kind != 0) j = (j + 1) % n;
             (*collect)[i].next_gemv = j;
+            (*collect)[i].nx_W = (*collect)[j].g.W; (*collect)[i].nx_ldw = (*collect)[j].g.ldw;
+            (*collect)[i].nx_N = (*collect)[j].g.N; (*collect)[i].nx_K = (*collect)[j].g.K;
         }
         return 0;
     }
@@ -611,9 +640,19 @@ static int run_megakernel(mb200_model* m, int rows, int B, int n_splits_self, in
     mp.sync_counter = m->g_megasync.as<unsigned int>(); mp.error_flag = m->g_megasync.as<int>() + 8;
     mp.max_steps = max_steps; mp.row_slot = m->g_rowslot.as<int>();
     mp.trace = m->mega_trace.p ? m->mega_trace.as<unsigned long long>() : nullptr; mp.trace_step = 8;
+    if (!m->mega_ev[0]) { MB_CUDA_CHECK(cudaEventCreate(&m->mega_ev[0])); MB_CUDA_CHECK(cudaEventCreate(&m->mega_ev[1])); }
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 2, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaEventRecord(m->mega_ev[0], st));
     MB_TRY(launch_megakernel(mp, m->num_sms, st));
+    MB_CUDA_CHECK(cudaEventRecord(m->mega_ev[1], st));
     MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 1, m->g_megasync.as<int>() + 8, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 3, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
     MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        MB_CUDA_CHECK(cudaEventElapsedTime(&ms, m->mega_ev[0], m->mega_ev[1]));
+        m->mega_ms += ms; m->mega_launches += 1; m->mega_tokens += m->h_flag[3] - m->h_flag[2];
+    }
     MB_REQUIRE(m->h_flag[1] == 0, m->h_flag[1] == 1 ? "megakernel grid barrier timed out" : "megakernel weight copy timed out");
     return 0;
 }
@@ -695,9 +734,43 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
 
     MB_TRY(launch_prompt_scan(m->g_ids.as<long long>(), ids_ld, B, P, m->g_vflags.as<unsigned char>(), sc.ts_start, sc.ts_end,
                               m->g_lastts.as<int>(), st));
-    MB_TRY(decoder_prefill(m, rows, P, m->g_prefill_ids.as<long long>(), gp->position_rule, st));
-    MB_TRY(final_logits(m, rows, m->p_x.as<float>() + (size_t)(P - 1) * d, (long long)P * d, st, false));
-    MB_TRY(launch_sample(sample_params(m, rows), B, st, false));
+    // prefill + first token: ~230 small launches.  The first call of a given (rows, P) shape runs eagerly (it may allocate);
+    // from the second call on the same sequence is replayed as one CUDA graph (sequential windows reuse a few prompt lengths).
+    {
+        auto run_prefill = [&](cudaStream_t s) -> int {
+            MB_TRY(decoder_prefill(m, rows, P, m->g_prefill_ids.as<long long>(), gp->position_rule, s));
+            MB_TRY(final_logits(m, rows, m->p_x.as<float>() + (size_t)(P - 1) * d, (long long)P * d, s, false));
+            MB_TRY(launch_sample(sample_params(m, rows), B, s, false));
+            return 0;
+        };
+        const auto pkey = std::make_tuple(rows, (int)P, (int)gp->position_rule);
+        auto seen = m->prefill_seen.find(pkey);
+        if (seen == m->prefill_seen.end()) {
+            m->prefill_seen[pkey] = 1;
+            MB_TRY(run_prefill(st));
+        } else {
+            auto git = m->prefill_graphs.find(pkey);
+            if (git == m->prefill_graphs.end()) {
+                if (!m->cap_stream) MB_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+                MB_CUDA_CHECK(cudaStreamSynchronize(st));
+                cudaGraph_t graph;
+                MB_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+                const long long before = g_launch_count;
+                int s = run_prefill(m->cap_stream);
+                cudaError_t e = cudaStreamEndCapture(m->cap_stream, &graph);
+                const long long nodes = g_launch_count - before;
+                g_launch_count = before;
+                if (s) return s;
+                MB_CUDA_CHECK(e);
+                cudaGraphExec_t exec;
+                MB_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+                cudaGraphDestroy(graph);
+                git = m->prefill_graphs.emplace(pkey, std::make_pair(exec, nodes)).first;
+            }
+            MB_CUDA_CHECK(cudaGraphLaunch(git->second.first, st));
+            g_launch_count += git->second.second;
+        }
+    }
 
     // ---- token loop, persistent path: every remaining token in ONE cooperative launch ----
     if (mega_eligible(m, rows) && gp->max_length - (P + 1) > 0) {
@@ -847,5 +920,14 @@ extern "C" int mb200_model_read_trace(mb200_model* m, uint64_t* out, int32_t n_p
     MB_REQUIRE(m && out && m->mega_trace.p && n_phases <= 128, "trace not enabled");
     MB_CUDA_CHECK(cudaDeviceSynchronize());
     MB_CUDA_CHECK(cudaMemcpy(out, m->mega_trace.p, (size_t)n_phases * 6 * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Measurement hook: CUDA-event totals of the persistent token-loop kernel since the last reset:
+// out[0] = launches, out[1] = total device milliseconds, out[2] = tokens decoded inside those launches.
+extern "C" int mb200_model_mega_stats(mb200_model* m, double* out, int32_t reset) {
+    MB_REQUIRE(m && out, "null argument");
+    out[0] = (double)m->mega_launches; out[1] = m->mega_ms; out[2] = (double)m->mega_tokens;
+    if (reset) { m->mega_launches = 0; m->mega_ms = 0.0; m->mega_tokens = 0; }
     return 0;
 }

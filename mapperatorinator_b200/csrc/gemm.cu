@@ -5,6 +5,8 @@
 // token-major buffer, see RowMap), Whisper q/k/v/out/fc1/fc2 in encoder + prefill, DiT qkv/out/fc1/fc2/adaLN.
 //   A: [M, K] via RowMap (K contiguous), W: [N, K] row-major (torch Linear layout), C/R: [M, N] via RowMap.
 // Tile 128x128x16, 256 threads, 8x8 micro-tile, double-buffered shared memory with register prefetch.
+#include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -46,12 +48,14 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_kernel(GemmParams p) {
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
     float4 ra[2], rw[2];
+    const int k_lo_ = p.splitk > 1 ? blockIdx.z * p.k_per_split : 0;
+    const int k_hi_ = p.splitk > 1 ? min(p.K, k_lo_ + p.k_per_split) : p.K;
     auto gload = [&](int k0) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            int k = k0 + lk;
-            ra[h] = (a_ok[h] && k < p.K) ? __ldg(reinterpret_cast<const float4*>(a_ptr[h] + k)) : make_float4(0, 0, 0, 0);
-            rw[h] = (w_ok[h] && k < p.K) ? __ldg(reinterpret_cast<const float4*>(w_ptr[h] + k)) : make_float4(0, 0, 0, 0);
+            int k = k_lo_ + k0 + lk;
+            ra[h] = (a_ok[h] && k < k_hi_) ? __ldg(reinterpret_cast<const float4*>(a_ptr[h] + k)) : make_float4(0, 0, 0, 0);
+            rw[h] = (w_ok[h] && k < k_hi_) ? __ldg(reinterpret_cast<const float4*>(w_ptr[h] + k)) : make_float4(0, 0, 0, 0);
         }
     };
     auto sstore = [&](int buf) {
@@ -63,7 +67,9 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_kernel(GemmParams p) {
         }
     };
 
-    const int nk = (p.K + BK - 1) / BK;
+    const int k_lo = p.splitk > 1 ? blockIdx.z * p.k_per_split : 0;
+    const int k_hi = p.splitk > 1 ? min(p.K, k_lo + p.k_per_split) : p.K;
+    const int nk = (k_hi - k_lo + BK - 1) / BK;
     gload(0);
     sstore(0);
     __syncthreads();
@@ -90,6 +96,22 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_kernel(GemmParams p) {
     }
 
     // ---- epilogue --------------------------------------------------------------------------------------------------
+    if (p.splitk > 1) {      // raw partial sums; gemm_splitk_reduce_kernel finishes the job
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+            if (m >= p.M) continue;
+            float* wrow = p.splitk_ws + ((long long)blockIdx.z * p.M + m) * p.N;
+#pragma unroll
+            for (int jh = 0; jh < 2; ++jh)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int nn = n0 + jh * 64 + tx * 4 + j;
+                    if (nn < p.N) wrow[nn] = acc[i][jh * 4 + j];
+                }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -113,6 +135,20 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_kernel(GemmParams p) {
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(GemmParams p) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)p.M * p.N) return;
+    const long long m = idx / p.N;
+    const int n = (int)(idx - m * p.N);
+    float v = 0.f;
+    for (int z = 0; z < p.splitk; ++z) v += p.splitk_ws[((long long)z * p.M + m) * p.N + n];   // fixed order
+    if (p.bias) v += __ldg(p.bias + n);
+    v = apply_act(v, p.act) * p.alpha;
+    if (p.gate) v *= __ldg(p.gate + (m / p.gate_rpb) * p.gate_ld + n);
+    if (p.R.ptr) v += p.R.row(m)[n];
+    p.C.row(m)[n] = v;
 }
 
 // ---- skinny variant: M <= 64 rows (decoder prefill of a 17-50 token prompt) ------------------------------------------------
@@ -195,11 +231,39 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     MB_REQUIRE((reinterpret_cast<uintptr_t>(p.A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0,
                "GEMM operands must be 16-byte aligned");
     if (p.M <= 0 || p.N <= 0) return 0;
-    if (p.M <= 64) {
+    if (tc_gemm_eligible(p) && launch_gemm_tc(p, stream) == 0) return 0;      // tensor cores (3xTF32); falls through on failure
+    static const int small_m_mode = [] { const char* e = getenv("MB200_SMALLM"); return e ? atoi(e) : 2; }();   // 0 tile, 1 skinny, 2 split-K
+    if (p.M <= 64 && small_m_mode == 1) {
         gemm_skinny_kernel<<<(p.N + SK_ROWS - 1) / SK_ROWS, 128, 0, stream>>>(p);
         MB_LAUNCH_CHECK();
         ++g_launch_count;
         return 0;
+    }
+    const int tiles_m = (int)((p.M + BM - 1) / BM), tiles_n = (p.N + BN - 1) / BN;
+    if ((long long)tiles_m * tiles_n < 100 && small_m_mode == 2 && p.K >= 64) {
+        // fewer output tiles than SMs (decoder prefill, a single encoder window, DiT conditioning): split K over enough CTAs to
+        // fill the machine — these problems are weight-streaming bound, not FLOP bound
+        static float* ws = nullptr;
+        static size_t ws_bytes = 0;
+        const int tiles = tiles_m * tiles_n;
+        int splits = std::max(1, std::min((148 + tiles - 1) / tiles, p.K / 32));
+        const int kps = ((p.K + splits - 1) / splits + BK - 1) / BK * BK;
+        splits = (p.K + kps - 1) / kps;
+        const size_t need = (size_t)splits * p.M * p.N * sizeof(float);
+        if (!ws) {   // fixed-size workspace, allocated once: captured graphs hold this pointer
+            ws_bytes = (size_t)64 << 20;
+            MB_CUDA_CHECK(cudaMalloc(&ws, ws_bytes));
+        }
+        if (splits > 1 && need <= ws_bytes) {
+            GemmParams q = p;
+            q.splitk_ws = ws; q.splitk = splits; q.k_per_split = kps;
+            gemm_f32_kernel<<<dim3(tiles_n, tiles_m, splits), 256, 0, stream>>>(q);
+            MB_LAUNCH_CHECK();
+            gemm_splitk_reduce_kernel<<<(unsigned)(((long long)p.M * p.N + 255) / 256), 256, 0, stream>>>(q);
+            MB_LAUNCH_CHECK();
+            g_launch_count += 2;
+            return 0;
+        }
     }
     dim3 grid((p.N + BN - 1) / BN, (unsigned)((p.M + BM - 1) / BM));
     gemm_f32_kernel<<<grid, 256, 0, stream>>>(p);

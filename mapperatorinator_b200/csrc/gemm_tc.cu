@@ -1,0 +1,373 @@
+// Tensor-core GEMM for the dense phases (encoder layers, conv stem, DiT blocks): tcgen05.mma kind::tf32 with fp32-grade
+// accuracy through the 3xTF32 split
+//        A.W^T  ~=  Ahi.Whi^T + Ahi.Wlo^T + Alo.Whi^T ,   x = xhi + xlo,  xhi = rn_tf32(x), xlo = rn_tf32(x - xhi).
+// Both parts are rounded to nearest tf32 (cvt.rna) — weights once at load, activations by a tiny elementwise pass — because the
+// tensor core would otherwise TRUNCATE the low 13 bits, and truncation bias adds up linearly over K.  Accumulation is fp32 in TMEM.  Measured error vs fp64 is ~1e-6 relative — the same order as an fp32 FMA chain of that
+// length — which is what bit-exact greedy decoding against the fp32 reference needs; plain TF32 (1e-3) flips tokens.
+//
+// Structure (one 128x128 output tile per CTA, 192 threads):
+//   warp 0 / lane 0 : TMA producer — 4 tiles per k-block (A, Alo, W, Wlo; 128 rows x 32 floats, SWIZZLE_128B) into a 3-stage ring
+//   warp 1 / lane 0 : MMA issuer   — 12 x tcgen05.mma (128x128x8) per k-block into a 128-column fp32 TMEM accumulator,
+//                     tcgen05.commit frees the stage / publishes the accumulator
+//   warps 2..5      : epilogue     — tcgen05.ld (32 lanes x 32 columns per warp and pass) -> bias / activation / gate /
+//                     residual (same GemmParams epilogue as gemm.cu) -> global
+// A may be any RowMap (im2col-free conv over the padded buffer, batched rows) via a 3-D tensor map.
+// Every wait is bounded: on a timeout the kernel sets an error flag and falls through, it can never hang the GPU.
+#include <cuda.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <map>
+#include <tuple>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mb200 {
+
+struct Tf32Mirror { const float* hi; const float* lo; };
+std::unordered_map<const float*, Tf32Mirror> g_w_lo;   // weight matrix -> its tf32 hi / lo arrays (filled by the engines at finalize)
+int g_tc_enabled = 1;
+
+namespace {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KB
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;         // A, Alo, W, Wlo
+
+struct TcBarriers {
+    unsigned long long full[TC_STAGES];
+    unsigned long long empty[TC_STAGES];
+    unsigned long long tmem_full;
+    unsigned int tmem_base;
+    int pad;
+};
+
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool bar_wait(unsigned long long* bar, unsigned parity, int* err) {
+    for (long long spin = 0; spin < (1ll << 22); ++spin) {
+        unsigned ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    atomicExch(err, 3);
+    return false;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024B>>4 | version 1 | layout 2
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3FFF);
+    d |= (unsigned long long)1 << 16;
+    d |= (unsigned long long)(1024 >> 4) << 32;
+    d |= (unsigned long long)1 << 46;
+    d |= (unsigned long long)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"l"(__cvta_generic_to_shared(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
+                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo, GemmParams p, int a_rpb, int* err) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * TC_BN;
+    const long long m0 = (long long)blockIdx.y * TC_BM;
+    const int nkb = (p.K + TC_BK - 1) / TC_BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars->full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars->empty[s])));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars->tmem_full)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&bars->tmem_base)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int a_b = a_rpb > 0 ? (int)(m0 / a_rpb) : 0;
+            const int a_t = a_rpb > 0 ? (int)(m0 - (long long)a_b * a_rpb) : (int)m0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TC_STAGES;
+                const unsigned ph = (kb / TC_STAGES) & 1;
+                if (!bar_wait(&bars->empty[s], ph ^ 1, err)) break;
+                unsigned char* st = smem + s * TC_STAGE_BYTES;
+                const unsigned fb = s32(&bars->full[s]);
+                asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(fb), "r"(TC_STAGE_BYTES) : "memory");
+                const int k0 = kb * TC_BK;
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(s32(st)), "l"(&map_a), "r"(k0), "r"(a_t), "r"(a_b), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(s32(st + TC_TILE_BYTES)), "l"(&map_alo), "r"(k0), "r"(a_t), "r"(a_b), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(s32(st + 2 * TC_TILE_BYTES)), "l"(&map_w), "r"(k0), "r"(n0), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(s32(st + 3 * TC_TILE_BYTES)), "l"(&map_wlo), "r"(k0), "r"(n0), "r"(fb) : "memory");
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 128, M = 128
+            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_BN >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+            bool ok = true;
+            for (int kb = 0; kb < nkb && ok; ++kb) {
+                const int s = kb % TC_STAGES;
+                const unsigned ph = (kb / TC_STAGES) & 1;
+                ok = bar_wait(&bars->full[s], ph, err);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned base = s32(smem + s * TC_STAGE_BYTES);
+#pragma unroll
+                for (int sub = 0; sub < TC_BK / 8; ++sub) {
+                    const unsigned off = sub * 32;       // 8 tf32 = 32 bytes along K inside the 128-byte swizzle atom
+                    const unsigned long long a_hi = umma_desc(base + off), a_lo = umma_desc(base + TC_TILE_BYTES + off);
+                    const unsigned long long w_hi = umma_desc(base + 2 * TC_TILE_BYTES + off), w_lo = umma_desc(base + 3 * TC_TILE_BYTES + off);
+                    umma_tf32(tmem, a_hi, w_hi, idesc, (kb > 0 || sub > 0) ? 1u : 0u);
+                    umma_tf32(tmem, a_hi, w_lo, idesc, 1u);
+                    umma_tf32(tmem, a_lo, w_hi, idesc, 1u);
+                }
+                umma_commit(&bars->empty[s]);            // frees the stage once these MMAs have read it
+            }
+            umma_commit(&bars->tmem_full);               // accumulator complete
+        }
+    } else {
+        const bool ok = bar_wait(&bars->tmem_full, 0, err);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int lg = warp & 3;                          // TMEM lane group this warp may access
+        const long long m = m0 + lg * 32 + lane;
+        float* crow = nullptr;
+        const float* rrow = nullptr;
+        const float* grow = nullptr;
+        if (ok && m < p.M) {
+            crow = p.C.row(m);
+            rrow = p.R.ptr ? p.R.row(m) : nullptr;
+            grow = p.gate ? p.gate + (m / p.gate_rpb) * p.gate_ld : nullptr;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            unsigned v[32];
+            const unsigned taddr = tmem + ((unsigned)(lg * 32) << 16) + (unsigned)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (crow) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < p.N) {
+                        float x = __uint_as_float(v[j]);
+                        if (p.bias) x += __ldg(p.bias + n);
+                        x = apply_act(x, p.act) * p.alpha;
+                        if (grow) x *= __ldg(grow + n);
+                        if (rrow) x += rrow[n];
+                        crow[n] = x;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
+}
+
+// x = hi + lo with hi = round-to-nearest tf32(x) and lo = round-to-nearest tf32(x - hi).  Rounding (not truncating) both parts
+// matters: truncation errors all point toward zero and add up linearly over K (measured 8e-6 relative at K = 3072, 70x the
+// fp32 FMA kernel); rounded parts leave unbiased ~2^-22 errors that grow like sqrt(K).
+__device__ __forceinline__ float rn_tf32(float x) {
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__global__ void tf32_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 h, l;
+    h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
+    l.x = rn_tf32(v.x - h.x); l.y = rn_tf32(v.y - h.y); l.z = rn_tf32(v.z - h.z); l.w = rn_tf32(v.w - h.w);
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows x K] fp32, K contiguous, optional batching: dims {K, rpb, batches}; box {32, 128, 1}; 128-byte swizzle; OOB reads give 0
+int make_map(CUtensorMap* out, const float* base, long long K, long long rows_per_batch, long long ld, long long batches, long long bstride,
+             int rank) {
+    EncodeTiledFn fn = encode_fn();
+    MB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows_per_batch, (cuuint64_t)batches};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(bstride > 0 ? bstride : ld * rows_per_batch) * 4};
+    cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+
+float* g_alo = nullptr;          // activation "lo" scratch (same layout as the A buffer it mirrors)
+size_t g_alo_bytes = 0;
+int* g_tc_err = nullptr;
+
+}  // namespace
+
+// One-time self test of the tensor-core path against a host fp64 product.  If the tcgen05 pipeline misbehaves on this
+// driver / device the path is switched off LOUDLY and every GEMM stays on the fp32 SIMT kernel (same results, slower).
+static int g_tc_tested = 0;
+static void tc_self_test() {
+    g_tc_tested = 1;
+    const int M = 512, N = 128, K = 96;
+    std::vector<float> a((size_t)M * K), w((size_t)N * K), c((size_t)M * N);
+    unsigned s = 12345u;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)((s >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+    for (auto& v : a) v = rnd();
+    for (auto& v : w) v = rnd();
+    float *da = nullptr, *dw = nullptr, *dc = nullptr;
+    bool ok = cudaMalloc(&da, a.size() * 4) == cudaSuccess && cudaMalloc(&dw, w.size() * 4) == cudaSuccess && cudaMalloc(&dc, c.size() * 4) == cudaSuccess;
+    if (ok) {
+        cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
+        GemmParams g{};
+        g.A = plain_map(da, K); g.W = dw; g.ldw = K; g.C = plain_map(dc, N); g.alpha = 1.f; g.gate_rpb = 1; g.M = M; g.N = N; g.K = K;
+        ok = tc_register_weight(dw, (long long)N * K) == 0 && launch_gemm_tc(g, nullptr) == 0 && cudaDeviceSynchronize() == cudaSuccess &&
+             tc_gemm_error() == 0;
+        if (ok) {
+            cudaMemcpy(c.data(), dc, c.size() * 4, cudaMemcpyDeviceToHost);
+            double worst = 0;
+            for (int m = 0; m < M; m += 37)
+                for (int n = 0; n < N; n += 5) {
+                    double r = 0;
+                    for (int k = 0; k < K; ++k) r += (double)a[(size_t)m * K + k] * (double)w[(size_t)n * K + k];
+                    worst = std::max(worst, std::fabs(r - (double)c[(size_t)m * N + n]));
+                }
+            ok = worst < 1e-4;
+        }
+    }
+    if (da) cudaFree(da);
+    if (dw) { tc_unregister_weight(dw); cudaFree(dw); }
+    if (dc) cudaFree(dc);
+    if (!ok) {
+        g_tc_enabled = 0;
+        fprintf(stderr, "[mapperatorinator_b200] WARNING: tcgen05 GEMM self-test FAILED — tensor-core path disabled, using the fp32 SIMT GEMM\n");
+        cudaGetLastError();
+    }
+}
+
+bool tc_gemm_eligible(const GemmParams& p) {
+    if (g_tc_enabled && !g_tc_tested) tc_self_test();
+    if (!g_tc_enabled || p.splitk > 1) return false;
+    if (p.M < 512 || p.N < 64 || p.K < 32 || p.K % 4 != 0) return false;
+    if (g_w_lo.find(p.W) == g_w_lo.end()) return false;
+    if (p.A.rpb != 0 && (p.A.rpb % TC_BM) != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(p.A.ptr) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15) || (p.A.ld % 4) || (p.ldw % 4)) return false;
+    if (p.A.rpb != 0 && (p.A.bstride % 4)) return false;
+    return true;
+}
+
+int launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
+    const Tf32Mirror wm = g_w_lo.at(p.W);
+    // extent of the buffer A rows live in (rows may overlap: im2col-free conv) and its lo mirror
+    const long long batches = p.A.rpb ? (p.M + p.A.rpb - 1) / p.A.rpb : 1;
+    const long long rpb = p.A.rpb ? p.A.rpb : p.M;
+    const long long extent = (batches - 1) * (p.A.rpb ? p.A.bstride : 0) + (rpb - 1) * p.A.ld + p.K;
+    const long long n4 = (extent + 3) / 4;
+    if ((size_t)n4 * 32 > g_alo_bytes) {       // hi and lo halves
+        if (g_alo) cudaFree(g_alo);
+        g_alo_bytes = std::max((size_t)n4 * 32, (size_t)512 << 20);
+        MB_CUDA_CHECK(cudaMalloc(&g_alo, g_alo_bytes));
+    }
+    float* a_hi = g_alo;
+    float* a_lo = g_alo + n4 * 4;
+    if (!g_tc_err) { MB_CUDA_CHECK(cudaMalloc(&g_tc_err, 4)); MB_CUDA_CHECK(cudaMemset(g_tc_err, 0, 4)); }
+    tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(p.A.ptr, a_hi, a_lo, n4);
+    MB_LAUNCH_CHECK();
+    CUtensorMap ma, mal, mw, mwl;
+    MB_REQUIRE(make_map(&ma, a_hi, p.K, rpb, p.A.ld, batches, p.A.rpb ? p.A.bstride : 0, 3) == 0, "tensor map Ahi");
+    MB_REQUIRE(make_map(&mal, a_lo, p.K, rpb, p.A.ld, batches, p.A.rpb ? p.A.bstride : 0, 3) == 0, "tensor map Alo");
+    MB_REQUIRE(make_map(&mw, wm.hi, p.K, p.N, p.ldw, 1, 0, 2) == 0, "tensor map Whi");
+    MB_REQUIRE(make_map(&mwl, wm.lo, p.K, p.N, p.ldw, 1, 0, 2) == 0, "tensor map Wlo");
+    static bool configured = false;
+    const int smem = TC_STAGES * TC_STAGE_BYTES + (int)sizeof(TcBarriers) + 1024;
+    if (!configured) {
+        MB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid((p.N + TC_BN - 1) / TC_BN, (unsigned)((p.M + TC_BM - 1) / TC_BM));
+    gemm_tf32x3_kernel<<<grid, TC_THREADS, smem, stream>>>(ma, mal, mw, mwl, p, p.A.rpb, g_tc_err);
+    MB_LAUNCH_CHECK();
+    g_launch_count += 2;
+    return 0;
+}
+
+// error flag of the tensor-core path (0 = fine, 3 = a pipeline wait timed out); checked by tests and the engines' self-test
+int tc_gemm_error() {
+    if (!g_tc_err) return 0;
+    int h = 0;
+    cudaMemcpy(&h, g_tc_err, 4, cudaMemcpyDeviceToHost);
+    return h;
+}
+
+void tc_unregister_weight(const float* w) {
+    auto it = g_w_lo.find(w);
+    if (it == g_w_lo.end()) return;
+    cudaFree(const_cast<float*>(it->second.hi));      // hi and lo share one allocation
+    g_w_lo.erase(it);
+}
+
+// lo mirror of a weight matrix (called once per weight at load; the owner unregisters it before freeing the weight)
+int tc_register_weight(const float* w, long long numel) {
+    tc_unregister_weight(w);      // a recycled device address must never inherit a stale mirror
+    float* buf = nullptr;
+    const long long n4 = (numel + 3) / 4;
+    MB_CUDA_CHECK(cudaMalloc(&buf, (size_t)n4 * 32));
+    tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256>>>(w, buf, buf + n4 * 4, n4);
+    MB_LAUNCH_CHECK();
+    g_w_lo[w] = Tf32Mirror{buf, buf + n4 * 4};
+    return 0;
+}
+
+}  // namespace mb200

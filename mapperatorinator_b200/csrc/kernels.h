@@ -18,8 +18,19 @@ struct GemmParams {
     int gate_rpb;
     RowMap R;               // residual (ptr == null -> none)
     int M, N, K;
+    // split-K (set by launch_gemm for small M): CTA z accumulates k in [z*k_per_split, ...) into ws[z][M][N]; a second kernel
+    // reduces the partials in fixed order and applies the epilogue
+    float* splitk_ws; int splitk; int k_per_split;
 };
 int launch_gemm(const GemmParams& p, cudaStream_t stream);
+// gemm_tc.cu — tcgen05 3xTF32 path (fp32-grade accuracy on the tensor cores); launch_gemm dispatches to it for large problems
+// whose weight matrix has a registered tf32 "lo" mirror
+extern int g_tc_enabled;
+bool tc_gemm_eligible(const GemmParams& p);
+int launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
+int tc_register_weight(const float* w, long long numel);
+void tc_unregister_weight(const float* w);
+int tc_gemm_error();
 
 // ---- norm.cu ---------------------------------------------------------------------------------------------------------
 // y[m, :] = LN(x[m, :]) * w + b                       (affine; w/b may be null)
@@ -165,6 +176,7 @@ constexpr int MEGA_WBUF_FLOATS = 19712;       // 77 KB weight slice per buffer (
 struct MegaPhase {                            // one dependent micro-phase of a token (built on the host)
     int kind;                                 // 0 GEMV, 1 split-KV attention, 2 logits chain + token selection
     int next_gemv;                            // index of the next GEMV phase (wraps into the next token)
+    const float* nx_W; long long nx_ldw; int nx_N, nx_K;   // its weight matrix, so the prefetch needs no extra global reads
     GemvParams g;
     DecAttnParams a;
 };

@@ -36,6 +36,17 @@ def gemm(a, w, bias=None, act="none", alpha=1.0, residual=None, gate=None, gate_
     return out
 
 
+def gemm_tc(a, w, bias=None, act="none", alpha=1.0, residual=None):
+    """Same contract as `gemm`, forced through the tcgen05 3xTF32 kernel."""
+    lib = _lib.load()
+    a, w = _f32c(a), _f32c(w)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    _lib.check(lib.mb200_op_gemm_tc(_ptr(a), K, _ptr(w), K, _ptr(out), N, _ptr(bias), ACT[act], float(alpha), _ptr(residual), N, M, N, K, _stream()))
+    return out
+
+
 def layernorm(x, weight=None, bias=None, shift=None, scale=None, rows_per_batch=1, eps=1e-5):
     lib = _lib.load()
     x = _f32c(x)

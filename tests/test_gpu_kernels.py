@@ -30,6 +30,22 @@ def test_gemm_epilogues(M, N, K, act):
     assert torch.allclose(out, ref, rtol=2e-5, atol=2e-5), (out - ref).abs().max()
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 768, 768), (640, 3072, 388), (512, 130, 3072), (2048, 2304, 768), (1500, 768, 2304)])
+def test_gemm_tcgen05_3xtf32_matches_fp64(M, N, K):
+    """The tensor-core path must be fp32-grade (3xTF32 split, fp32 TMEM accumulation): error vs an fp64 product of the same
+    order as the fp32 SIMT kernel's, far below plain TF32 (~1e-3)."""
+    from mapperatorinator_b200 import ops
+    g = _g(M + N + K)
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K)
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ref = F.gelu(a.double() @ w.double().T + bias.double()) * 0.5 + res.double()
+    tc = ops.gemm_tc(a.cuda(), w.cuda(), bias.cuda(), "gelu", 0.5, res.cuda()).cpu().double()
+    simt = ops.gemm(a.cuda(), w.cuda(), bias.cuda(), "gelu", 0.5, res.cuda()).cpu().double()
+    scale = ref.abs().max().item()
+    e_tc, e_simt = (tc - ref).abs().max().item() / scale, (simt - ref).abs().max().item() / scale
+    assert e_tc <= max(5e-6, 3 * e_simt), (e_tc, e_simt)       # fp32-grade: same order as the fp32 FMA kernel (plain TF32: ~1e-3)
+
+
 @pytest.mark.parametrize("dim", [128, 768, 1024])
 def test_layernorm_affine_and_modulate(dim):
     from mapperatorinator_b200 import ops
