@@ -59,6 +59,10 @@ def prompt_for(i: int, streams) -> list:
     return base if i == 0 else base + streams[i - 1][-32:]
 
 
+# one `ncu --set full` capture of decode_megakernel<1> (63 tokens): 25.765 GB read + 7.2 MB written (profiles/r1_megakernel_ncu.md)
+MEGA_DRAM_BYTES_PER_LAUNCH = 25_765_018_000 + 7_231_744
+
+
 def gen_kwargs(i: int, n_windows: int, P: int) -> dict:
     ms = 8184.0
     return dict(do_sample=False, num_beams=1, top_p=0.9, top_k=0, cfg_scale=1.0, timeshift_bias=0, types_first=True, temperature=0.9,
@@ -108,7 +112,7 @@ def run_reference(args, rank: int, world: int) -> None:
     if rank != 0:
         return
     from oracle import generate as gen_oracle
-    cores = args.cpu_threads or min(os.cpu_count() or 1, 32)
+    cores = args.cpu_threads or min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     cfg = v29_model_config()
     layout = TokenLayout.from_json(os.path.join(ROOT, "tests", "golden", "tokenizer_v29.json"))
@@ -162,7 +166,7 @@ def main() -> None:
     ap.add_argument("--tc", type=int, default=int(os.environ.get("MB200_TC", "1")), help="1 = tcgen05 3xTF32 GEMMs where eligible, 0 = fp32 SIMT GEMM everywhere")
     ap.add_argument("--mega", type=int, default=1, help="1 = persistent token-loop megakernel (default), 0 = CUDA-graph replay per token")
     ap.add_argument("--cpu-threads", type=int, default=int(os.environ.get("MB200_CPU_THREADS", "0")),
-                    help="torch threads of the CPU arm (0 = min(cores, 32): more threads only slow a batch-1 decoder down)")
+                    help="torch threads of the CPU arm (0 = min(cores, 16): measured best on the GPU box; 32+ threads slow a batch-1 decoder down)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -271,8 +275,10 @@ def main() -> None:
         bytes_per_launch = (w_bytes + kv_bytes) * tok_per_launch
         achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9
         roofline = {"bound": "hbm", "kernel": "decode_megakernel<1> (persistent cooperative kernel: all layers of all tokens of one generate() call)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "bytes_per_launch": bytes_per_launch, "us_per_launch": us_per_launch, "tokens_per_launch": tok_per_launch,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": MEGA_DRAM_BYTES_PER_LAUNCH if abs(tok_per_launch - 63.0) < 1e-6 else None,
+                    "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 63-token launch (profiles/r1_megakernel_ncu.md)",
+                    "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "us_per_launch": us_per_launch, "tokens_per_launch": tok_per_launch,
                     "us_per_token": us_per_launch / tok_per_launch, "bytes_per_token": w_bytes + kv_bytes,
                     "share_of_step": mega[1] / (ms_resident), "token_floor_us": (w_bytes + kv_bytes) / (peak * 1e3)}
     else:
@@ -294,7 +300,7 @@ def main() -> None:
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import generate as gen_oracle
-        cores = args.cpu_threads or min(os.cpu_count() or 1, 32)
+        cores = args.cpu_threads or min(os.cpu_count() or 1, 16)
         torch.set_num_threads(cores)
         sd_cpu = init_model_state_dict(cfg, 0)
         cs, ctoks = [], 0
