@@ -1,8 +1,8 @@
 // Per-token decode path of the osuT5 decoder (reference: HF WhisperDecoderLayer x12 + proj_out called once per token by
 // GenerationMixin._sample, ~330 launches + a host sync per token — SURVEY §3.2).  Here one token = 8 kernels per layer:
 //   gemv[LN1 -> q|k|v, k/v written in place into the self cache]  ->  split-KV self attention  ->
-//   gemv[combine splits -> out_proj + residual]  ->  gemv[LN2 -> cross q]  ->  split-KV cross attention  ->
-//   gemv[combine -> out_proj + residual]  ->  gemv[LN3 -> fc1 + GELU]  ->  gemv[fc2 + residual]
+//   gemv[out_proj + residual]  ->  gemv[LN2 -> cross q]  ->  split-KV cross attention (+ merge)  ->
+//   gemv[out_proj + residual]  ->  gemv[LN3 -> fc1 + GELU]  ->  gemv[fc2 + residual]
 // then gemv[final LN -> proj_out] and ONE kernel that runs the whole logits-processor chain (server.py:106-134 +
 // HF min_new_tokens / top-k / top-p), selects the token, tests the EOS set, appends to `ids`, and writes the next step's
 // embedding.  No host synchronisation per token; every step-varying scalar is read from GenState in device memory.
@@ -20,13 +20,13 @@ constexpr int GEMV_THREADS = 128, GEMV_WARPS = GEMV_THREADS / 32;
 
 template <int NB>
 __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(GemvParams p) {
-    extern __shared__ __align__(16) float xs[];   // [NB][K] activations, then NB*H*(n_splits+1) combine scratch
+    extern __shared__ __align__(16) float xs[];   // [NB][K] activations, then 32 floats of LayerNorm reduction scratch
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
     pdl_wait();
     const int cur_pos = p.st ? p.st->cur_len - 1 : 0;
     for (int b0 = 0; b0 < p.B; b0 += NB) {
-        gemv_stage_x<NB>(p, b0, xs, xs + NB * p.K, tid, GEMV_THREADS);
+        gemv_stage_x<NB, GEMV_THREADS>(p, b0, xs, xs + NB * p.K, tid);
         __syncthreads();
         for (int n = blockIdx.x * GEMV_WARPS + warp; n < p.N; n += gridDim.x * GEMV_WARPS)
             gemv_row<NB, true>(p, n, p.W + (long long)n * p.ldw, xs, b0, lane, cur_pos);
@@ -107,10 +107,9 @@ int launch_with_attrs(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_
 int launch_gemv(const GemvParams& p, cudaStream_t stream, bool pdl) {
     MB_REQUIRE(p.K % 4 == 0 && p.ldw % 4 == 0, "GEMV K / ldw must be multiples of 4");
     MB_REQUIRE(p.xmode != X_LAYERNORM || p.K <= 1024, "fused LayerNorm prologue supports K <= 1024");
-    MB_REQUIRE(p.xmode != X_ATTN_COMBINE || p.K == p.H * 64, "attention-combine prologue needs K == H*64");
     if (p.B <= 0 || p.N <= 0) return 0;
     int nb = p.B >= 8 ? 8 : (p.B > 4 ? 8 : (p.B > 2 ? 4 : p.B));
-    const size_t smem = ((size_t)nb * p.K + (p.xmode == X_ATTN_COMBINE ? (size_t)nb * p.H * (p.n_splits + 1) : 0)) * sizeof(float);
+    const size_t smem = ((size_t)nb * p.K + 32) * sizeof(float);
     const int blocks = (p.N + GEMV_WARPS - 1) / GEMV_WARPS;
     static bool configured = false;
     if (!configured) {
@@ -132,6 +131,7 @@ int launch_gemv(const GemvParams& p, cudaStream_t stream, bool pdl) {
 
 int launch_decode_attention(const DecAttnParams& p, cudaStream_t stream, bool pdl) {
     MB_REQUIRE(p.chunk > 0 && p.chunk <= 128, "decode attention chunk must be in (0, 128]");
+    MB_REQUIRE(p.out && p.ticket, "decode attention needs the merged-output buffer and its tickets");
     if (p.rows <= 0) return 0;
     g_prof_class = 1;
     return launch_with_attrs(decode_attention_kernel, dim3(p.n_splits, p.H, p.rows), dim3(128), 0, stream, pdl, p);

@@ -13,133 +13,97 @@ __device__ __forceinline__ float2 ldcg2(const float* p) { return __ldcg(reinterp
 __device__ __forceinline__ int ld_state(const int* p) { return __ldcg(p); }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// activation staging for the GEMV family: xs[NB][K] <- LayerNorm(x) | merged split-KV partials | x
+// activation staging for the GEMV family: xs[NB][K] <- LayerNorm(x) | x
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NB>
-__device__ __forceinline__ void gemv_stage_x(const GemvParams& p, int b0, float* xs, float* scratch /* NB*H*(n_splits+1) */, int tid,
-                                             int nthreads) {
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+template <int NB, int NT>
+__device__ __forceinline__ void gemv_stage_x(const GemvParams& p, int b0, float* xs, float* scratch /* >= 32 floats */,
+                                             int tid, unsigned long long* dbg = nullptr /* trace: loads-landed stamp */) {
+    constexpr int nthreads = NT;
+    const int lane = tid & 31, warp = tid >> 5;
     const int K = p.K, K4 = K >> 2;
     if (p.xmode == X_LAYERNORM) {
-        for (int bb = warp; bb < NB; bb += nwarps) {
-            float* dst = xs + bb * K;
-            if (b0 + bb >= p.B) { for (int k = lane; k < K; k += 32) dst[k] = 0.f; continue; }
+        // All warps share the row(s): float4 index idx = c*32 + lane belongs to chunk c in [0, 8) (K <= 1024).  Each chunk is reduced
+        // by one warp, the 8 chunk partials by a fixed tree, so the arithmetic does not depend on the caller's warp count (the
+        // per-kernel path with 4 warps and the megakernel with 16 stay bit-identical).  Per lane only 1-2 float4 triples are live:
+        // the old one-warp-per-row form held 24 float4 in flight, which (a) serialised ~3000 cycles on one warp and (b) under the
+        // megakernel's 128-register cap spilled freshly loaded values to local memory, i.e. waited for them.
+        constexpr int NW = NT / 32;
+        static_assert(NW == 1 || NW == 2 || NW == 4 || NW == 8 || NW == 16 || NW == 32, "warp count must be a power of two");
+        constexpr int CPW = NW >= 8 ? 1 : 8 / NW;          // chunks per warp inside a row
+        constexpr int RG = NW >= 8 ? NW / 8 : 1;           // rows staged per round
+        float* red = scratch;                              // [2][RG][8]
+        const float inv = 1.0f / (float)K;
+        for (int g0 = 0; g0 < NB; g0 += RG) {
+            const int rl = (warp * CPW) >> 3, bb = g0 + rl, c0 = (warp * CPW) & 7;
+            const bool row_ok = rl < RG && bb < NB && b0 + bb < p.B;
             const float* src = p.x + (long long)(b0 + bb) * p.x_ld;
-            float4 v[8], lw[8], lb[8];
-            // every load of this prologue (activations + LayerNorm affine) is issued before the first reduction: one L2 round trip
+            float4 v[CPW], lw[CPW], lb[CPW];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int idx = i * 32 + lane;
-                v[i] = idx < K4 ? ldcg4(src + idx * 4) : make_float4(0, 0, 0, 0);
-                lw[i] = idx < K4 ? __ldg(reinterpret_cast<const float4*>(p.ln_w) + idx) : make_float4(0, 0, 0, 0);
-                lb[i] = idx < K4 ? __ldg(reinterpret_cast<const float4*>(p.ln_b) + idx) : make_float4(0, 0, 0, 0);
+            for (int i = 0; i < CPW; ++i) {
+                const int idx = (c0 + i) * 32 + lane;
+                const bool ok = row_ok && idx < K4;
+                v[i] = ok ? ldcg4(src + idx * 4) : make_float4(0, 0, 0, 0);
+                lw[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.ln_w) + idx) : make_float4(0, 0, 0, 0);
+                lb[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.ln_b) + idx) : make_float4(0, 0, 0, 0);
             }
-            float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-            const float inv = 1.0f / (float)K;
-            const float mean = warp_sum(s) * inv;
-            float q = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i * 32 + lane < K4) {
-                    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-                    q += (a * a + b * b) + (c * c + d * d);
-                }
+            for (int i = 0; i < CPW; ++i) {
+                const float sc = warp_sum((v[i].x + v[i].y) + (v[i].z + v[i].w));
+                if (lane == 0 && rl < RG) red[rl * 8 + c0 + i] = sc;
             }
-            const float rstd = rsqrtf(warp_sum(q) * inv + p.eps);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int idx = i * 32 + lane;
-                if (idx < K4) {
-                    const float4 w = lw[i], bsv = lb[i];
-                    float4 o;
-                    o.x = (v[i].x - mean) * rstd * w.x + bsv.x; o.y = (v[i].y - mean) * rstd * w.y + bsv.y;
-                    o.z = (v[i].z - mean) * rstd * w.z + bsv.z; o.w = (v[i].w - mean) * rstd * w.w + bsv.w;
-                    reinterpret_cast<float4*>(dst)[idx] = o;
-                }
+            if (dbg && tid == 0) *dbg = (unsigned long long)clock64();
+            __syncthreads();
+            float mean = 0.f;
+            if (rl < RG) {
+                const float* r = red + rl * 8;
+                mean = (((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))) * inv;
             }
-        }
-    } else if (p.xmode == X_ATTN_COMBINE) {
-        // merge the split-KV partials: x[b, h*64+d] = sum_s w_s o_s[d] / sum_s w_s l_s, w_s = exp(m_s - max m).
-        // Stage A: one thread per (row, head) computes the split weights (independent loads, two L2 round trips);
-        // stage B: one thread per element gathers its n_splits partials with all loads in flight at once.
-        const int S = p.n_splits;
-        if (S <= 8) {
-            // single round trip: every element thread fetches its (<= 8) partials AND the (m, l) pairs of its head in one batch and
-            // derives the split weights itself (a few redundant expf beat a second dependent L2 access)
-            for (int e = tid; e < NB * K; e += nthreads) {
-                const int bb = e / K, c = e - bb * K, h = c >> 6, d = c & 63;
-                float val = 0.f;
-                if (b0 + bb < p.B) {
-                    const long long base = ((long long)(b0 + bb) * p.H + h) * S;
-                    float2 ml[8]; float po[8];
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        ml[s] = s < S ? ldcg2(p.part_ml + (base + s) * 2) : make_float2(-INFINITY, 0.f);
-                        po[s] = s < S ? __ldcg(p.part_o + (base + s) * 64 + d) : 0.f;
-                    }
-                    float mmax = -INFINITY;
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) if (s < S) mmax = fmaxf(mmax, ml[s].x);
-                    float num = 0.f, den = 0.f;
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        if (s < S && ml[s].y > 0.f) {
-                            const float w = expf(ml[s].x - mmax);
-                            num = fmaf(w, po[s], num);
-                            den = fmaf(w, ml[s].y, den);
-                        }
-                    }
-                    val = den > 0.f ? num / den : 0.f;
+            for (int i = 0; i < CPW; ++i) {
+                const bool ok = row_ok && (c0 + i) * 32 + lane < K4;
+                float q = 0.f;
+                if (ok) {
+                    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                    q = (a * a + b * b) + (c * c + d * d);
                 }
-                xs[e] = val;
-            }
-        } else {
-            for (int idx = tid; idx < NB * p.H; idx += nthreads) {
-                const int bb = idx / p.H, h = idx - bb * p.H;
-                float* wv = scratch + idx * (S + 1);
-                float den = 0.f;
-                if (b0 + bb < p.B) {
-                    const float* ml = p.part_ml + ((long long)(b0 + bb) * p.H + h) * S * 2;
-                    float mmax = -INFINITY;
-    #pragma unroll 8
-                    for (int s = 0; s < S; ++s) mmax = fmaxf(mmax, __ldcg(ml + s * 2));
-    #pragma unroll 8
-                    for (int s = 0; s < S; ++s) {
-                        const float2 v = ldcg2(ml + s * 2);
-                        const float w = v.y > 0.f ? expf(v.x - mmax) : 0.f;
-                        wv[s] = w;
-                        if (v.y > 0.f) den = fmaf(w, v.y, den);
-                    }
-                } else {
-                    for (int s = 0; s < S; ++s) wv[s] = 0.f;
-                }
-                wv[S] = den;
+                q = warp_sum(q);
+                if (lane == 0 && rl < RG) red[RG * 8 + rl * 8 + c0 + i] = q;
             }
             __syncthreads();
-            for (int e = tid; e < NB * K; e += nthreads) {
-                const int bb = e / K, c = e - bb * K, h = c >> 6, d = c & 63;
-                const float* wv = scratch + (bb * p.H + h) * (S + 1);
-                const float* po = p.part_o + ((long long)(b0 + bb) * p.H + h) * S * 64 + d;
-                float num = 0.f;
-                if (b0 + bb < p.B) {
-    #pragma unroll 8
-                    for (int s = 0; s < S; ++s) {
-                        const float w = wv[s];
-                        if (w != 0.f) num = fmaf(w, __ldcg(po + s * 64), num);
+            if (rl < RG && bb < NB) {
+                const float* r = red + RG * 8 + rl * 8;
+                const float rstd = rsqrtf((((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))) * inv + p.eps);
+                float* dst = xs + bb * K;
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) {
+                    const int idx = (c0 + i) * 32 + lane;
+                    if (idx < K4) {
+                        float4 o = make_float4(0, 0, 0, 0);
+                        if (row_ok) {
+                            o.x = (v[i].x - mean) * rstd * lw[i].x + lb[i].x; o.y = (v[i].y - mean) * rstd * lw[i].y + lb[i].y;
+                            o.z = (v[i].z - mean) * rstd * lw[i].z + lb[i].z; o.w = (v[i].w - mean) * rstd * lw[i].w + lb[i].w;
+                        }
+                        reinterpret_cast<float4*>(dst)[idx] = o;
                     }
                 }
-                const float den = wv[S];
-                xs[e] = den > 0.f ? num / den : 0.f;
             }
+            // no barrier between rounds: the next round's first write to either half of `red` is ordered behind this round's reads
+            // of that half by the barrier in between
         }
     } else {
-        for (int e = tid; e < NB * K4; e += nthreads) {
-            int bb = e / K4, c = e - bb * K4;
-            float4 v = make_float4(0, 0, 0, 0);
-            if (b0 + bb < p.B) v = ldcg4(p.x + (long long)(b0 + bb) * p.x_ld + c * 4);
-            reinterpret_cast<float4*>(xs)[e] = v;
+        // plain rows: a thread's loads are all issued before its first store (one L2 round trip for up to 4*NT float4)
+        for (int e0 = tid; e0 < NB * K4; e0 += 4 * nthreads) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * nthreads, bb = e / K4, c = e - bb * K4;
+                v[u] = (e < NB * K4 && b0 + bb < p.B) ? ldcg4(p.x + (long long)(b0 + bb) * p.x_ld + c * 4) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * nthreads;
+                if (e < NB * K4) reinterpret_cast<float4*>(xs)[e] = v[u];
+            }
         }
     }
 }
@@ -205,6 +169,62 @@ __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float
     }
 }
 
+// Merge of the split-KV partials, done ONCE per (row, head) by whichever split arrives last (threadfence-reduction pattern):
+// out[r, h*64+d] = sum_s w_s o_s[d] / sum_s w_s l_s, w_s = exp(m_s - max m), splits visited in index order, so the result does not
+// depend on which CTA happens to be last.  (It used to be a prologue of the following GEMV, i.e. all 148 CTAs re-did it, each
+// pulling every partial out of L2: 2-6 us per layer on the token's critical path.)
+__device__ __forceinline__ void decode_attention_merge(const DecAttnParams& p, int h, int r, float* stat, int tid) {
+    __threadfence();                                   // this CTA's partial is visible before its ticket
+    __syncthreads();
+    int* ticket = p.ticket + r * p.H + h;
+    if (tid == 0) stat[0] = (atomicAdd(ticket, 1) == p.n_splits - 1) ? 1.f : 0.f;
+    __syncthreads();
+    if (stat[0] == 0.f) return;                        // uniform across the CTA
+    __threadfence();
+    if (tid < 64) {
+        const int S = p.n_splits;
+        const long long base = ((long long)r * p.H + h) * S;
+        const float* ml = p.part_ml + base * 2;
+        const float* po = p.part_o + base * 64 + tid;
+        float num = 0.f, den = 0.f;
+        if (S <= 8) {                                  // every load in flight at once
+            float2 mv[8]; float ov[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                mv[s] = s < S ? ldcg2(ml + s * 2) : make_float2(-INFINITY, 0.f);
+                ov[s] = s < S ? __ldcg(po + s * 64) : 0.f;
+            }
+            float mmax = -INFINITY;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) if (s < S) mmax = fmaxf(mmax, mv[s].x);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (s < S && mv[s].y > 0.f) {
+                    const float w = expf(mv[s].x - mmax);
+                    num = fmaf(w, ov[s], num);
+                    den = fmaf(w, mv[s].y, den);
+                }
+            }
+        } else {                                       // contexts beyond 512 tokens: two rolled passes
+            float mmax = -INFINITY;
+#pragma unroll 1
+            for (int s = 0; s < S; ++s) mmax = fmaxf(mmax, __ldcg(ml + s * 2));
+#pragma unroll 1
+            for (int s = 0; s < S; ++s) {
+                const float2 mv = ldcg2(ml + s * 2);
+                const float ov = __ldcg(po + s * 64);
+                if (mv.y > 0.f) {
+                    const float w = expf(mv.x - mmax);
+                    num = fmaf(w, ov, num);
+                    den = fmaf(w, mv.y, den);
+                }
+            }
+        }
+        p.out[(long long)r * p.out_ld + h * 64 + tid] = den > 0.f ? num / den : 0.f;
+    }
+    if (tid == 0) *ticket = 0;                         // ready for the next phase that uses this (row, head)
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // split-KV decode attention for one (split s, head h, row r); NW warps cooperate; smem: sc[128], red[NW][64], stat[2]
 // ---------------------------------------------------------------------------------------------------------------------
@@ -216,6 +236,7 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
     const long long out_idx = ((long long)r * p.H + h) * p.n_splits + s;
     if (k_begin >= k_end) {
         if (tid == 0) { p.part_ml[out_idx * 2] = -INFINITY; p.part_ml[out_idx * 2 + 1] = 0.f; }
+        decode_attention_merge(p, h, r, stat, tid);
         return;
     }
     const float* kb = p.kc + (long long)slot * p.row_stride + h * 64;
@@ -309,6 +330,7 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
         p.part_o[out_idx * 64 + tid] = v;
         if (tid == 0) { p.part_ml[out_idx * 2] = stat[0]; p.part_ml[out_idx * 2 + 1] = stat[1]; }
     }
+    decode_attention_merge(p, h, r, stat, tid);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -349,8 +371,10 @@ struct SampleSmem {
 };
 
 // The whole logits-processor chain + token selection + append for batch row b (one CTA of SAMPLE_THREADS threads).
+// Deliberately NOT inlined and with rolled vocabulary loops: it runs once per token on one CTA, and inside the persistent
+// megakernel its code must not push the per-layer phases out of the 32 KB L1.5 instruction cache.
 // Returns after the "last CTA" bookkeeping; the caller decides how the grid synchronises afterwards.
-__device__ __forceinline__ void sample_body(const SampleParams& p, int b, SampleSmem& sm) {
+static __device__ __noinline__ void sample_body(const SampleParams& p, int b, SampleSmem& sm) {
     float* s = sm.s;
     int* sidx = sm.sidx;
     float* scratch = sm.scratch;
@@ -365,7 +389,7 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, int b, Sample
     const bool suppress_eos = st_min_new > 0 && (L - st_prompt_len) < st_min_new;
 
     // (0)+(1): min_new_tokens EOS suppression, then classifier-free guidance on raw logits
-    for (int v = tid; v < V; v += SAMPLE_THREADS) {
+    _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
         float x;
         const bool eos = (p.vflags[v] & VF_EOS) != 0;
         if (c.use_cfg) {
@@ -391,7 +415,7 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, int b, Sample
         }
     }
     __syncthreads();
-    for (int v = tid; v < V; v += SAMPLE_THREADS) {
+    _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
         float x = s[v];
         if (v >= c.ts_start && v < c.ts_end) {
             if (lts >= 0 && v < c.ts_start + lts) x = -INFINITY;
@@ -404,21 +428,21 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, int b, Sample
     // (5) LookbackBias
     if (c.lookback_on) {
         if (!c.types_first) {
-            for (int v = c.lookback_start + tid; v < c.lookback_end; v += SAMPLE_THREADS) s[v] = -INFINITY;
+            _Pragma("unroll 1") for (int v = c.lookback_start + tid; v < c.lookback_end; v += SAMPLE_THREADS) s[v] = -INFINITY;
             __syncthreads();
         } else {
             float* ls_cur = p.last_scores + ((long long)(st_step & 1) * B + b) * V;
             const float* ls_prev = p.last_scores + ((long long)((st_step + 1) & 1) * B + b) * V;
-            for (int v = tid; v < V; v += SAMPLE_THREADS) ls_cur[v] = s[v];
+            _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) ls_cur[v] = s[v];
             const long long last_tok = L > 0 ? __ldcg(ids_row + (L - 1)) : -1;
             const bool timed = last_tok >= 0 && (p.vflags[last_tok] & VF_TIMED);
             if (st_has_last && timed) {
                 float m_last = -INFINITY, m_cur = -INFINITY;
-                for (int v = tid; v < V; v += SAMPLE_THREADS) { m_last = fmaxf(m_last, __ldcg(ls_prev + v)); m_cur = fmaxf(m_cur, s[v]); }
+                _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) { m_last = fmaxf(m_last, __ldcg(ls_prev + v)); m_cur = fmaxf(m_cur, s[v]); }
                 m_last = block_reduce(m_last, true, scratch);
                 m_cur = block_reduce(m_cur, true, scratch);
                 float z_last = 0.f, z_cur = 0.f, e_last = 0.f, o_cur = 0.f;
-                for (int v = tid; v < V; v += SAMPLE_THREADS) {
+                _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
                     float pl = expf(__ldcg(ls_prev + v) - m_last);
                     float pc = expf(s[v] - m_cur);
                     z_last += pl; z_cur += pc;
@@ -433,7 +457,7 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, int b, Sample
                 const float prob_event = 1.f - prob_eos;
                 const float sc = 1.f / ((o_cur / z_cur) * prob_event + prob_eos);
                 const float extra = fminf(fmaxf((sc - 1.f) * prob_eos / prob_event, 0.f), 1.f);
-                for (int v = tid; v < V; v += SAMPLE_THREADS) {
+                _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
                     float pr;
                     if (v == c.lookback_start) pr = extra;
                     else if (v >= c.lookback_start && v < c.lookback_end) pr = 0.f;
@@ -450,7 +474,7 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, int b, Sample
     if (!c.do_sample) {
         // argmax, first index on ties (torch.argmax)
         float best = -INFINITY; int bi = 0x7fffffff;
-        for (int v = tid; v < V; v += SAMPLE_THREADS) {
+        _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
             float x = s[v];
             if (x > best || (x == best && v < bi)) { best = x; bi = v; }
         }
@@ -473,7 +497,7 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, int b, Sample
         chosen = sm.chosen_sh;
     } else {
         // sort ascending (bitonic over VMAX slots, padding = +inf at the top so real entries keep ascending order)
-        for (int v = tid; v < VMAX; v += SAMPLE_THREADS) { sidx[v] = v; if (v >= V) s[v] = INFINITY; }
+        _Pragma("unroll 1") for (int v = tid; v < VMAX; v += SAMPLE_THREADS) { sidx[v] = v; if (v >= V) s[v] = INFINITY; }
         __syncthreads();
         const bool need_sort = c.top_k > 0 || c.top_p < 1.0f;
         if (need_sort) {
@@ -497,16 +521,16 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, int b, Sample
                 int kk = min(c.top_k, V);
                 float thr = s[V - kk];
                 __syncthreads();
-                for (int v = tid; v < V; v += SAMPLE_THREADS) if (s[v] < thr) s[v] = -INFINITY;
+                _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) if (s[v] < thr) s[v] = -INFINITY;
                 __syncthreads();
             }
         }
         // softmax over the (possibly sorted) entries
         float m = -INFINITY;
-        for (int v = tid; v < V; v += SAMPLE_THREADS) m = fmaxf(m, s[v]);
+        _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) m = fmaxf(m, s[v]);
         m = block_reduce(m, true, scratch);
         float z = 0.f;
-        for (int v = tid; v < V; v += SAMPLE_THREADS) z += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m);
+        _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) z += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m);
         z = block_reduce(z, false, scratch);
         // serial inclusive scan by one warp-strided pass is overkill for V<=4096: thread 0 walks (V adds) — negligible vs
         // a decoder step, and gives a fixed summation order.

@@ -23,6 +23,7 @@ namespace {
 
 constexpr int MEGA_THREADS = SAMPLE_THREADS;            // 512
 constexpr int MEGA_WARPS = MEGA_THREADS / 32;
+constexpr int MEGA_TRACE_SLOTS = 12;
 constexpr int MEGA_NB_MAX = 2;                          // decoder rows handled: the kernel is instantiated for 1 and 2
 constexpr int XS_FLOATS = MEGA_NB_MAX * 3072;
 
@@ -34,8 +35,9 @@ struct __align__(16) MegaSmem {
         struct { float sc[128]; float red[4][64]; float stat[2]; } attn;
     } u;
     MegaPhase phase[2];
+    SampleParams sample_params;                 // shared copy: the chain is an out-of-line call and must not pin `mp` in local memory
     int ctrl[8];                                // all_finished, error, cur_len, prompt_len, encoder slot of row 0 / row 1
-    float combine[MEGA_NB_MAX * 16 * 33];           // split weights for the attention-combine prologue (H <= 16, n_splits <= 32)
+    float ln_red[32];                           // LayerNorm chunk partials
     unsigned long long mbar[2];
 };
 
@@ -97,13 +99,12 @@ __device__ __forceinline__ bool wait_weights(unsigned long long* bar, unsigned p
 }
 
 __device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
+    // SM cycle counter: every stamp of a trace comes from CTA 0 (one SM), so clock64 is consistent and far finer than %globaltimer
+    return (unsigned long long)clock64();
 }
 #define MEGA_TRACE(slot)                                                                              \
     do {                                                                                              \
-        if (tracing && tid == 0) mp.trace[(long long)pi * 6 + (slot)] = gtimer();                     \
+        if (tracing && tid == 0) mp.trace[(long long)pi * MEGA_TRACE_SLOTS + (slot)] = gtimer();                     \
     } while (0)
 
 __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int target, int* error_flag) {
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
     const int cta = blockIdx.x, G = gridDim.x;
 
     if (tid == 0) {
+        sm.sample_params = mp.sample;
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -171,27 +173,41 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
         for (int pi = 0; pi < mp.n_phases; ++pi) {
             const MegaPhase& ph = sm.phase[cur];
             MEGA_TRACE(0);
-            // next phase's descriptor: requested now into a register, parked in shared memory at the end of the phase, so its
-            // latency is not serialised in front of this phase's own loads
+            // next phase's descriptor: copied global -> shared asynchronously (cp.async, no register is held across the phase: under the
+            // 128-register cap a held value was spilled to local memory right after its load, i.e. the phase WAITED for it) and
+            // drained just before the end-of-phase barrier
             constexpr int DESC_WORDS = (int)(sizeof(MegaPhase) / 4);
             static_assert(DESC_WORDS <= MEGA_THREADS, "descriptor must fit one word per thread");
-            int desc_word = 0;
-            if (tid < DESC_WORDS) desc_word = reinterpret_cast<const int*>(&mp.phases[pi + 1 < mp.n_phases ? pi + 1 : 0])[tid];
+            if (tid < DESC_WORDS) {
+                const int* src = reinterpret_cast<const int*>(&mp.phases[pi + 1 < mp.n_phases ? pi + 1 : 0]) + tid;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(reinterpret_cast<int*>(&sm.phase[cur ^ 1]) + tid)), "l"(src) : "memory");
+            }
             if (ph.kind == 0) {
                 const int buf = g_idx & 1;
                 int r0, r1;
                 cta_rows(ph.g.N, cta, G, r0, r1);
-                // epilogue operands (bias, residual) of this warp's rows are requested first, together with the activations
-                float bias_v[4], r_v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                // epilogue operands (bias, residual) of this warp's rows are requested first, together with the activations:
+                // lane j*NB + b holds them for the warp's j-th row and batch row b (no per-row register arrays -> one copy of the
+                // row code; the whole token loop has to stay inside the 32 KB L1.5 instruction cache)
+                constexpr int OPS_ROWS = 32 / MEGA_NB;
+                float bias_pref = 0.f, r_pref = 0.f;
+                {
+                    const int j = lane / MEGA_NB, b = lane - j * MEGA_NB;
                     const int n = r0 + warp + j * MEGA_WARPS;
-                    bias_v[j] = 0.f; r_v[j] = 0.f;
-                    if (n < r1) gemv_row_operands<MEGA_NB>(ph.g, n, 0, lane, bias_v[j], r_v[j]);
+                    if (n < r1 && b < ph.g.B) {
+                        if (ph.g.bias) bias_pref = __ldg(ph.g.bias + n);
+                        if (ph.g.R) r_pref = __ldcg(ph.g.R + (long long)b * ph.g.r_ld + n);
+                    }
                 }
-                gemv_stage_x<MEGA_NB>(ph.g, 0, sm.u.xs, sm.combine, tid, MEGA_THREADS);
-                MEGA_TRACE(1);
-                __syncthreads();
+                // trace mode runs the staging twice through the SAME code: pass 0 (slots 8, 9, 10) is what production pays, pass 1
+                // (slots 6, 7, 1) repeats it with instruction cache / TLB / L2 state warm — the difference is fetch, not data, latency
+                for (int rep = tracing ? 0 : 1; rep < 2; ++rep) {
+                    MEGA_TRACE(rep ? 6 : 8);
+                    gemv_stage_x<MEGA_NB, MEGA_THREADS>(ph.g, 0, sm.u.xs, sm.ln_red, tid,
+                                                        tracing ? &mp.trace[(long long)pi * MEGA_TRACE_SLOTS + (rep ? 7 : 9)] : nullptr);
+                    MEGA_TRACE(rep ? 1 : 10);
+                    __syncthreads();
+                }
                 MEGA_TRACE(2);
                 // The next GEMV's weight slice is requested only now: measured on B200, issuing the ~5-9 MB bulk stream at
                 // the top of the phase queued this phase's few small latency-critical loads (activations, LN affine, bias)
@@ -201,15 +217,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                 wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, mp.error_flag);   // on a timeout the error flag ends the loop at the next token
                 MEGA_TRACE(3);
                 {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int n = r0 + warp + j * MEGA_WARPS;
-                        if (n < r1)
-                            gemv_row<MEGA_NB, false>(ph.g, n, sm.wbuf[buf] + (long long)(n - r0) * ph.g.K, sm.u.xs, 0, lane, cur_pos, true,
-                                                     bias_v[j], r_v[j]);
+                    int j = 0;
+#pragma unroll 1
+                    for (int n = r0 + warp; n < r1; n += MEGA_WARPS, ++j) {
+                        const bool pre = j < OPS_ROWS;
+                        const float bias_v = __shfl_sync(0xffffffffu, bias_pref, (j * MEGA_NB) & 31);
+                        const float r_v = __shfl_sync(0xffffffffu, r_pref, (j * MEGA_NB + (lane < MEGA_NB ? lane : 0)) & 31);
+                        gemv_row<MEGA_NB, false>(ph.g, n, sm.wbuf[buf] + (long long)(n - r0) * ph.g.K, sm.u.xs, 0, lane, cur_pos, pre, bias_v, r_v);
                     }
-                    for (int n = r0 + warp + 4 * MEGA_WARPS; n < r1; n += MEGA_WARPS)      // more than 64 rows per CTA (small K)
-                        gemv_row<MEGA_NB, false>(ph.g, n, sm.wbuf[buf] + (long long)(n - r0) * ph.g.K, sm.u.xs, 0, lane, cur_pos);
                 }
                 ++g_idx;
             } else if (ph.kind == 1) {
@@ -223,9 +238,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                     __syncthreads();
                 }
             } else {
-                if (cta < mp.sample.cfg->B) sample_body(mp.sample, cta, sm.u.sample);
+                if (cta < sm.sample_params.cfg->B) sample_body(sm.sample_params, cta, sm.u.sample);
             }
-            if (tid < DESC_WORDS) reinterpret_cast<int*>(&sm.phase[cur ^ 1])[tid] = desc_word;
+            asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
             MEGA_TRACE(4);
             sync_target += G;

@@ -62,6 +62,7 @@ struct mb200_model {
     // decoder workspaces
     DevBuf p_x, p_h, p_q, p_attn, p_ffn;          // prefill, sized rows * P
     DevBuf d_x, d_q, d_h, d_parto, d_partml, d_logits;   // decode step
+    DevBuf d_attn, d_ticket;            // merged attention heads [rows, d] and the per-(row, head) arrival counters of the split merge
     DevBuf g_state, g_cfg, g_vflags, g_ids, g_prefill_ids, g_keyvalid, g_leftpad, g_rowslot, g_finished, g_lastts, g_lastscores;
     int* h_flag = nullptr;              // pinned
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
@@ -74,7 +75,7 @@ struct mb200_model {
     bool use_mega = true;
     int num_sms = 0;
     DevBuf g_megasync;                  // [0] grid-barrier counter, [8] error flag
-    DevBuf mega_trace;                  // optional per-phase globaltimer stamps (option "mega_trace")
+    DevBuf mega_trace;                  // optional per-phase clock64 stamps (option "mega_trace")
     cudaEvent_t mega_ev[2] = {nullptr, nullptr};
     double mega_ms = 0.0; long long mega_launches = 0, mega_tokens = 0;   // CUDA-event time of every megakernel launch
     std::map<std::pair<int, int>, std::pair<DevBuf*, int>> mega_phases;   // (rows, n_splits_self) -> device phase table
@@ -317,6 +318,9 @@ extern "C" int mb200_model_finalize(mb200_model* m) {
         const int max_splits = std::max((c.tgt_seq_len + 63) / 64, (c.src_seq_len / 2 + 63) / 64);
         MB_TRY(m->d_parto.ensure((size_t)m->max_rows * c.heads * max_splits * 64 * sizeof(float)));
         MB_TRY(m->d_partml.ensure((size_t)m->max_rows * c.heads * max_splits * 2 * sizeof(float)));
+        MB_TRY(m->d_attn.ensure((size_t)m->max_rows * d * sizeof(float)));
+        MB_TRY(m->d_ticket.ensure((size_t)m->max_rows * c.heads * sizeof(int)));
+        MB_CUDA_CHECK(cudaMemset(m->d_ticket.p, 0, (size_t)m->max_rows * c.heads * sizeof(int)));
     }
     m->finalized = true;
     return 0;
@@ -542,7 +546,8 @@ static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaSt
     const int d = c.d_model, f = c.ffn_dim, H = c.heads, T = c.src_seq_len / 2;
     const GenState* gs = m->g_state.as<GenState>();
     float *x = m->d_x.as<float>(), *q = m->d_q.as<float>(), *hh = m->d_h.as<float>();
-    float *po = m->d_parto.as<float>(), *pml = m->d_partml.as<float>();
+    float *po = m->d_parto.as<float>(), *pml = m->d_partml.as<float>(), *attn = m->d_attn.as<float>();
+    int* ticket = m->d_ticket.as<int>();
     const int chunk = 64, n_splits_cross = (T + chunk - 1) / chunk;
     const long long self_row = (long long)c.tgt_seq_len * 2 * d;
     for (int l = 0; l < c.decoder_layers; ++l) {
@@ -563,11 +568,12 @@ static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaSt
             a.q = q; a.q_ld = d; a.kc = skv; a.vc = skv + d; a.row_stride = self_row; a.tok_stride = 2 * d; a.row_slot = nullptr;
             a.fixed_len = 0; a.st = gs; a.key_valid = m->g_keyvalid.as<unsigned char>(); a.key_valid_ld = c.tgt_seq_len;
             a.part_o = po; a.part_ml = pml; a.rows = rows; a.H = H; a.n_splits = n_splits_self; a.chunk = chunk;
+            a.out = attn; a.out_ld = d; a.ticket = ticket;
             MB_TRY(emit_attn(a));
         }
-        {   // combine -> out_proj + residual
-            GemvParams g = gemv_base(X_ATTN_COMBINE, w.wo, d, w.bo, d, d, rows, gs);
-            g.part_o = po; g.part_ml = pml; g.n_splits = n_splits_self; g.H = H;
+        {   // out_proj + residual (the heads were merged by the attention phase)
+            GemvParams g = gemv_base(X_PLAIN, w.wo, d, w.bo, d, d, rows, gs);
+            g.x = attn; g.x_ld = d;
             g.seg[0].out = x; g.seg[0].out_bs = d; g.R = x; g.r_ld = d;
             MB_TRY(emit_gemv(g));
         }
@@ -582,11 +588,12 @@ static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaSt
             a.q = q; a.q_ld = d; a.kc = ckv; a.vc = ckv + d; a.row_stride = (long long)T * 2 * d; a.tok_stride = 2 * d;
             a.row_slot = m->g_rowslot.as<int>(); a.fixed_len = T; a.st = gs; a.key_valid = nullptr;
             a.part_o = po; a.part_ml = pml; a.rows = rows; a.H = H; a.n_splits = n_splits_cross; a.chunk = chunk;
+            a.out = attn; a.out_ld = d; a.ticket = ticket;
             MB_TRY(emit_attn(a));
         }
         {
-            GemvParams g = gemv_base(X_ATTN_COMBINE, w.wo_c, d, w.bo_c, d, d, rows, gs);
-            g.part_o = po; g.part_ml = pml; g.n_splits = n_splits_cross; g.H = H;
+            GemvParams g = gemv_base(X_PLAIN, w.wo_c, d, w.bo_c, d, d, rows, gs);
+            g.x = attn; g.x_ld = d;
             g.seg[0].out = x; g.seg[0].out_bs = d; g.R = x; g.r_ld = d;
             MB_TRY(emit_gemv(g));
         }
@@ -725,6 +732,7 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
     MB_CUDA_CHECK(cudaMemcpyAsync(m->g_state.p, &gs, sizeof(gs), cudaMemcpyHostToDevice, st));
     MB_CUDA_CHECK(cudaMemcpyAsync(m->g_cfg.p, &sc, sizeof(sc), cudaMemcpyHostToDevice, st));
     MB_CUDA_CHECK(cudaMemsetAsync(m->g_finished.p, 0, m->max_rows, st));
+    MB_CUDA_CHECK(cudaMemsetAsync(m->d_ticket.p, 0, (size_t)m->max_rows * m->cfg.heads * sizeof(int), st));   // self-resetting; cleared in case a previous call aborted
     MB_CUDA_CHECK(cudaStreamSynchronize(st));   // host vectors go out of scope; the copies above are from pageable memory
 
     // partial buffers for the split-KV attentions
@@ -875,7 +883,7 @@ extern "C" int mb200_model_set_option(mb200_model* m, const char* name, int valu
     }
     if (!strcmp(name, "mega")) { m->use_mega = value != 0; return 0; }
     if (!strcmp(name, "mega_trace")) {
-        if (value) { MB_TRY(m->mega_trace.ensure(128 * 6 * 8)); MB_CUDA_CHECK(cudaMemset(m->mega_trace.p, 0, 128 * 6 * 8)); }
+        if (value) { MB_TRY(m->mega_trace.ensure(128 * 12 * 8)); MB_CUDA_CHECK(cudaMemset(m->mega_trace.p, 0, 128 * 12 * 8)); }
         return 0;
     }
     set_last_error(std::string("unknown option ") + name);
@@ -915,11 +923,11 @@ extern "C" int mb200_model_profile_step(mb200_model* m, int32_t rows, int32_t B,
     return 0;
 }
 
-// debug: copy the megakernel phase trace (option "mega_trace") to host: out[n_phases][6] nanosecond stamps
+// debug: copy the megakernel phase trace (option "mega_trace") to host: out[n_phases][12] SM-cycle stamps
 extern "C" int mb200_model_read_trace(mb200_model* m, uint64_t* out, int32_t n_phases) {
     MB_REQUIRE(m && out && m->mega_trace.p && n_phases <= 128, "trace not enabled");
     MB_CUDA_CHECK(cudaDeviceSynchronize());
-    MB_CUDA_CHECK(cudaMemcpy(out, m->mega_trace.p, (size_t)n_phases * 6 * 8, cudaMemcpyDeviceToHost));
+    MB_CUDA_CHECK(cudaMemcpy(out, m->mega_trace.p, (size_t)n_phases * 12 * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

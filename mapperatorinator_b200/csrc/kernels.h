@@ -117,7 +117,7 @@ struct SampleConfig {        // device-resident, rewritten by the host once per 
     int ids_ld;              // row stride of the ids buffer
 };
 
-enum XMode : int { X_PLAIN = 0, X_LAYERNORM = 1, X_ATTN_COMBINE = 2 };
+enum XMode : int { X_PLAIN = 0, X_LAYERNORM = 1 };
 
 struct GemvSeg {
     float* out;              // row b at out + b * out_bs + (pos ? (cur_len - 1) * pos_stride : 0)
@@ -132,7 +132,6 @@ struct GemvParams {
     int xmode;
     const float* x; long long x_ld;                 // PLAIN / LAYERNORM input rows
     const float* ln_w; const float* ln_b; float eps;
-    const float* part_o; const float* part_ml; int n_splits; int H;   // ATTN_COMBINE input
     const float* W; long long ldw; const float* bias;
     int K, N, B;
     int nseg; GemvSeg seg[3];
@@ -152,6 +151,8 @@ struct DecAttnParams {
     const unsigned char* key_valid; long long key_valid_ld;   // [rows, >=P] validity of prompt positions (null = all valid)
     float* part_o; float* part_ml;                  // [rows, H, n_splits, 64], [rows, H, n_splits, 2]
     int rows, H, n_splits, chunk;
+    float* out; long long out_ld;                   // merged heads [rows, H*64], written by the LAST split of each (row, head) to arrive
+    int* ticket;                                    // [rows, H] arrival counters, zero on entry, reset by the last arriver
 };
 int launch_decode_attention(const DecAttnParams& p, cudaStream_t stream, bool pdl);
 

@@ -23,22 +23,27 @@ prompt = torch.tensor([bench.prompt_for(0, [])])
 for _ in range(3):
     model.engine.generate([0], prompt, prompt.ne(0), layout, bench.gen_kwargs(0, 211, prompt.shape[1]))
 n = 12 * 8 + 2
-out = np.zeros((n, 6), dtype=np.uint64)
+out = np.zeros((n, 12), dtype=np.uint64)
 _lib.check(_lib.load().mb200_model_read_trace(model.engine.handle, out.ctypes.data, n))
-t = out.astype(np.int64)
+t = (out.astype(np.float64) / 1.965).astype(np.int64)      # SM cycles (clock64, 1965 MHz under load) -> ns
 names = ["qkv", "self_attn", "out", "q_c", "cross_attn", "out_c", "fc1", "fc2"]
 tot = t[-1, 5] - t[0, 0]
 print(f"token total {tot / 1e3:.1f} us over {n} phases")
-print("phase            own_stage  sync   pref+wait   math   barrier    total (us)")
-agg = {}
+print("phase            own_stage (issue, loads, rest)  sync   pref+wait   math   barrier    total (us)")
+agg, warm = {}, {}
 for i in range(n):
     nm = names[i % 8] if i < 96 else ("proj_out" if i == 96 else "sample")
     s0, s1, s2, s3, s4, s5 = (t[i, j] for j in range(6))
     if nm in ("self_attn", "cross_attn", "sample"):
-        seg = (0, 0, 0, s4 - s0, s5 - s4)
+        seg = (0, 0, 0, 0, 0, 0, s4 - s0, s5 - s4)
     else:
-        seg = (s1 - s0, s2 - s1, s3 - s2, s4 - s3, s5 - s4)
+        s6, s7, c0, c1, c2 = t[i, 6], t[i, 7], t[i, 8], t[i, 9], t[i, 10]
+        # trace mode stages twice: cold pass (c0 -> c2) then warm pass (s6 -> s1); report the cold one as the stage, warm beside it
+        ld = (c0 - s0, (c1 - c0) if c1 > 0 else 0, (c2 - c1) if c1 > 0 else c2 - c0)
+        warm.setdefault(nm, []).append(((s7 - s6) if s7 > 0 else 0, (s1 - s7) if s7 > 0 else s1 - s6))
+        seg = (c2 - s0,) + ld + (s2 - s1, s3 - s2, s4 - s3, s5 - s4)
     agg.setdefault(nm, []).append(seg + (s5 - s0,))
 for nm, v in agg.items():
     a = np.array(v, dtype=np.float64).mean(0) / 1e3
-    print(f"{nm:12s} x{len(v):3d} {a[0]:8.2f} {a[1]:8.2f} {a[2]:8.2f} {a[3]:7.2f} {a[4]:9.2f} {a[5]:8.2f}")
+    print(f"{nm:12s} x{len(v):3d} {a[0]:8.2f} ({a[1]:5.2f} {a[2]:5.2f} {a[3]:5.2f}) {a[4]:8.2f} {a[5]:8.2f} {a[6]:7.2f} {a[7]:9.2f} {a[8]:8.2f}"
+          + (f"   warm re-run of the staging: loads {np.mean([w[0] for w in warm[nm]]) / 1e3:.2f} rest {np.mean([w[1] for w in warm[nm]]) / 1e3:.2f}" if nm in warm else ""))
