@@ -162,10 +162,11 @@ int mb200_model_profile_step(mb200_model* m, int32_t rows, int32_t batch, int32_
                              void* cuda_stream);
 
 /* options "mega" (1 = persistent token-loop megakernel for <= 2 decoder rows, default) and "mega_trace" (1 = record
- * clock64 stamps of CTA 0 for every micro-phase of the 9th token); read them back as out[n_phases][12] SM cycles:
+ * clock64 stamps of CTA 0 for every micro-phase of the 9th token); read them back as out[n_phases][16] SM cycles:
  * {phase start, activations staged, CTA sync passed, weights landed, math done, grid barrier passed, staging start,
  *  LayerNorm loads landed (0 for non-LayerNorm phases), then the same three staging stamps {start, loads landed, staged} of a
- *  first (cold) pass that trace mode runs in front of the timed one, and one spare}. */
+ *  first (cold) pass that trace mode runs in front of the timed one, slot 11 = this warp's rows done, slot 12 = end of a first
+ *  (cold) pass over the rows that trace mode runs in front of the timed one; the rest spare}. */
 int mb200_model_read_trace(mb200_model* m, uint64_t* out, int32_t n_phases);
 /* CUDA-event totals of the persistent token-loop kernel (recorded on the launching stream around every launch):
  * out[0] = launches, out[1] = device milliseconds, out[2] = tokens decoded inside them; reset != 0 clears the counters. */

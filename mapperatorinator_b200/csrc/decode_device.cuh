@@ -174,13 +174,18 @@ __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float
 // depend on which CTA happens to be last.  (It used to be a prologue of the following GEMV, i.e. all 148 CTAs re-did it, each
 // pulling every partial out of L2: 2-6 us per layer on the token's critical path.)
 __device__ __forceinline__ void decode_attention_merge(const DecAttnParams& p, int h, int r, float* stat, int tid) {
-    __threadfence();                                   // this CTA's partial is visible before its ticket
+    // Arrival = ONE acq_rel atomic by thread 0 behind a CTA barrier (the same release/acquire shape as the grid barrier): the
+    // barrier orders every thread's partial stores before the release, and the last arriver's loads after the acquire.  No
+    // per-thread __threadfence (each one waits for the whole SM's outstanding stores).
     __syncthreads();
     int* ticket = p.ticket + r * p.H + h;
-    if (tid == 0) stat[0] = (atomicAdd(ticket, 1) == p.n_splits - 1) ? 1.f : 0.f;
+    if (tid == 0) {
+        int t;
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
+        stat[0] = (t == p.n_splits - 1) ? 1.f : 0.f;
+    }
     __syncthreads();
     if (stat[0] == 0.f) return;                        // uniform across the CTA
-    __threadfence();
     if (tid < 64) {
         const int S = p.n_splits;
         const long long base = ((long long)r * p.H + h) * S;
@@ -230,23 +235,26 @@ __device__ __forceinline__ void decode_attention_merge(const DecAttnParams& p, i
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NW>
 __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, int s, int h, int r, int slot, int L, int P, float* sc,
-                                                      float (*red)[64], float* stat, int tid) {
+                                                      float (*red)[64], float* stat, int tid, unsigned long long* dbg = nullptr) {
+#define ATTN_STAMP(i) do { if (dbg && tid == 0) dbg[i] = (unsigned long long)clock64(); } while (0)
     const int lane = tid & 31, warp = tid >> 5;
     const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
     const long long out_idx = ((long long)r * p.H + h) * p.n_splits + s;
-    if (k_begin >= k_end) {
+    if (k_begin >= k_end) {                               // empty split (uniform across the CTA): it still takes its ticket below
+        if (p.n_splits == 1) { if (tid < 64) p.out[(long long)r * p.out_ld + h * 64 + tid] = 0.f; return; }
         if (tid == 0) { p.part_ml[out_idx * 2] = -INFINITY; p.part_ml[out_idx * 2 + 1] = 0.f; }
-        decode_attention_merge(p, h, r, stat, tid);
-        return;
-    }
-    const float* kb = p.kc + (long long)slot * p.row_stride + h * 64;
-    const float* vb = p.vc + (long long)slot * p.row_stride + h * 64;
-    const int nk = k_end - k_begin;
+    } else {
+    // one 64-bit base per operand, 32-bit offsets from there (token strides and chunk offsets are small)
+    const int tok = (int)p.tok_stride;
+    const float* kb = p.kc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
+    const float* vb = p.vc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
+    const unsigned char* kv = p.key_valid ? p.key_valid + (long long)r * p.key_valid_ld + k_begin : nullptr;
+    const int nk = k_end - k_begin, n_prompt = P - k_begin;      // keys [0, n_prompt) of this split are prompt positions
 
     // scores: 8 lanes per key, each lane owns 8 of the 64 dims
     const int sub = lane & 7, kq = lane >> 3;
-    const float4 q0 = ldcg4(p.q + (long long)r * p.q_ld + h * 64 + sub * 8);
-    const float4 q1 = ldcg4(p.q + (long long)r * p.q_ld + h * 64 + sub * 8 + 4);
+    const float* qp = p.q + (long long)r * p.q_ld + h * 64 + sub * 8;
+    const float4 q0 = ldcg4(qp), q1 = ldcg4(qp + 4);
     // fixed trip count (chunk <= 128) so every K load of the chunk is in flight before the first shuffle
     constexpr int SC_ITERS = 128 / (4 * NW);
     float4 ka[SC_ITERS], kb4[SC_ITERS];
@@ -256,9 +264,9 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
         const int kk = it * 4 * NW + warp * 4 + kq;
         kvalid[it] = 1;
         if (kk < nk) {
-            const float* kr = kb + (long long)(k_begin + kk) * p.tok_stride + sub * 8;
+            const float* kr = kb + kk * tok + sub * 8;
             ka[it] = ldcg4(kr); kb4[it] = ldcg4(kr + 4);
-            if (p.key_valid && k_begin + kk < P) kvalid[it] = p.key_valid[(long long)r * p.key_valid_ld + k_begin + kk];
+            if (kv && kk < n_prompt) kvalid[it] = kv[kk];
         } else {
             ka[it] = make_float4(0, 0, 0, 0); kb4[it] = make_float4(0, 0, 0, 0);
         }
@@ -271,7 +279,7 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
 #pragma unroll
         for (int i = 0; i < PV_PRE; ++i) {
             const int kk = warp + 4 * i;
-            vpre[i] = kk < nk ? ldcg2(vb + (long long)(k_begin + kk) * p.tok_stride + lane * 2) : make_float2(0.f, 0.f);
+            vpre[i] = kk < nk ? ldcg2(vb + kk * tok + lane * 2) : make_float2(0.f, 0.f);
         }
     }
 #pragma unroll
@@ -286,51 +294,85 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
         d += __shfl_xor_sync(0xffffffffu, d, 4);
         if (kk < nk && sub == 0) sc[kk] = kvalid[it] ? d : -INFINITY;
     }
+    ATTN_STAMP(0);
     __syncthreads();
-    if (warp == 0) {
+    // Softmax statistics + o = sum_k p_k V_k in the four PV warps.  Every PV warp derives (m, l, p) itself — the same per-lane order
+    // (keys lane, lane+32, ...) and the same shuffle tree a single warp would use, so the bits do not depend on who computes them —
+    // instead of one warp computing them for everybody behind two CTA barriers.  Warp w owns keys w, w+4, ...; lane owns dims
+    // 2*lane, 2*lane+1: always four accumulation chains, whatever NW is (per-kernel path and megakernel stay bit-identical).
+    if (warp < 4) {
+        float pv[4];                                     // p of keys lane, lane+32, lane+64, lane+96
         float m = -INFINITY;
-        for (int i = lane; i < nk; i += 32) m = fmaxf(m, sc[i]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = lane + 32 * t;
+            pv[t] = i < nk ? sc[i] : -INFINITY;
+            m = fmaxf(m, pv[t]);
+        }
         m = warp_max(m);
         float l = 0.f;
-        for (int i = lane; i < nk; i += 32) {
-            float pv = (sc[i] == -INFINITY) ? 0.f : expf(sc[i] - m);
-            sc[i] = pv;
-            l += pv;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = lane + 32 * t;
+            pv[t] = (i < nk && pv[t] != -INFINITY) ? expf(pv[t] - m) : 0.f;
+            if (i < nk) l += pv[t];
         }
         l = warp_sum(l);
-        if (lane == 0) { stat[0] = m; stat[1] = l; }
-    }
-    __syncthreads();
-    // o = sum_k p_k V_k : warps 0..3 take keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1.  Always four accumulation chains,
-    // whatever NW is, so the per-kernel path and the megakernel produce bit-identical partials.
-    if (warp < 4) {
+        if (tid == 0) { stat[0] = m; stat[1] = l; }
+        ATTN_STAMP(1);
         float2 o = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < PV_PRE; ++i) {
-            const int kk = warp + 4 * i;
+            const int kk = warp + 4 * i;                 // < 32 for i < 8, in [32, 64) otherwise (warp <= 3)
+            const float pk = __shfl_sync(0xffffffffu, pv[i >> 3], kk & 31);
             if (kk < nk) {
-                const float pv = sc[kk];
-                o.x = fmaf(pv, vpre[i].x, o.x);
-                o.y = fmaf(pv, vpre[i].y, o.y);
+                o.x = fmaf(pk, vpre[i].x, o.x);
+                o.y = fmaf(pk, vpre[i].y, o.y);
             }
         }
-#pragma unroll 4
-        for (int kk = warp + 4 * PV_PRE; kk < nk; kk += 4) {      // chunks longer than 64 keys
-            const float pv = sc[kk];
-            const float2 vv = ldcg2(vb + (long long)(k_begin + kk) * p.tok_stride + lane * 2);
-            o.x = fmaf(pv, vv.x, o.x);
-            o.y = fmaf(pv, vv.y, o.y);
+        if (nk > 64) {                                   // chunks longer than 64 keys (uniform): loads issued first, then consumed
+#pragma unroll
+            for (int t = 2; t < 4; ++t) {
+                float2 vv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kk = 32 * t + warp + 4 * i;
+                    vv[i] = kk < nk ? ldcg2(vb + kk * tok + lane * 2) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kk = 32 * t + warp + 4 * i;
+                    const float pk = __shfl_sync(0xffffffffu, pv[t], kk & 31);
+                    if (kk < nk) {
+                        o.x = fmaf(pk, vv[i].x, o.x);
+                        o.y = fmaf(pk, vv[i].y, o.y);
+                    }
+                }
+            }
         }
         red[warp][lane * 2] = o.x;
         red[warp][lane * 2 + 1] = o.y;
     }
     __syncthreads();
+    if (p.n_splits == 1) {
+        // one split holds the whole context: the merge degenerates to o / l (w = exp(m - m) = 1: the same bits as the general path)
+        if (tid < 64) {
+            const float v = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+            const float num = fmaf(1.f, v, 0.f), den = fmaf(1.f, stat[1], 0.f);
+            p.out[(long long)r * p.out_ld + h * 64 + tid] = (stat[1] > 0.f && den > 0.f) ? num / den : 0.f;
+        }
+        return;
+    }
     if (tid < 64) {
         float v = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
         p.part_o[out_idx * 64 + tid] = v;
         if (tid == 0) { p.part_ml[out_idx * 2] = stat[0]; p.part_ml[out_idx * 2 + 1] = stat[1]; }
     }
+    }
+    ATTN_STAMP(2);
     decode_attention_merge(p, h, r, stat, tid);
+    ATTN_STAMP(3);
+#undef ATTN_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

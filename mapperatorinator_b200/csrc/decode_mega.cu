@@ -23,7 +23,7 @@ namespace {
 
 constexpr int MEGA_THREADS = SAMPLE_THREADS;            // 512
 constexpr int MEGA_WARPS = MEGA_THREADS / 32;
-constexpr int MEGA_TRACE_SLOTS = 12;
+constexpr int MEGA_TRACE_SLOTS = 16;
 constexpr int MEGA_NB_MAX = 2;                          // decoder rows handled: the kernel is instantiated for 1 and 2
 constexpr int XS_FLOATS = MEGA_NB_MAX * 3072;
 
@@ -73,17 +73,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // rows [r0, r1) of an N-row GEMV owned by CTA `cta` of `G`
-__device__ __forceinline__ void cta_rows(int N, int cta, int G, int& r0, int& r1) {
-    const int rpc = (N + G - 1) / G;
+__device__ __forceinline__ void cta_rows(int N, int cta, int rpc, int& r0, int& r1) {
     r0 = min(N, cta * rpc);
     r1 = min(N, r0 + rpc);
 }
 
 // thread 0: start streaming this CTA's weight rows of GEMV phase `ph` into wbuf[buf]
 __device__ __forceinline__ void prefetch_weights(const float* W, long long ldw, int N, int K, float* dst, unsigned long long* bar, int cta,
-                                                 int G) {
+                                                 int rpc) {
     int r0, r1;
-    cta_rows(N, cta, G, r0, r1);
+    cta_rows(N, cta, rpc, r0, r1);
     const unsigned bytes = (unsigned)(r1 - r0) * (unsigned)K * 4u;
     if (bytes == 0) { mbar_arrive(bar); return; }
     mbar_arrive_expect_tx(bar, bytes);
@@ -127,7 +126,8 @@ __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int ta
     __syncthreads();
 }
 
-template <int MEGA_NB>
+// TRACE = true is a separate instantiation used only by the phase-timeline tool: the production kernel carries no stamp code
+template <int MEGA_NB, bool TRACE>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams mp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MegaSmem& sm = *reinterpret_cast<MegaSmem*>(smem_raw);
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
     unsigned int sync_target = 0;
     if (tid == 0) {
         const MegaPhase* f = &mp.phases[mp.first_gemv];
-        prefetch_weights(f->g.W, f->g.ldw, f->g.N, f->g.K, sm.wbuf[0], &sm.mbar[0], cta, G);
+        prefetch_weights(f->g.W, f->g.ldw, f->g.N, f->g.K, sm.wbuf[0], &sm.mbar[0], cta, (f->g.N + G - 1) / G);
     }
 
     // phase descriptors are double-buffered in shared memory: slot `cur` is the phase being executed, slot `cur ^ 1` is
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
         __syncthreads();
         const int fin = sm.ctrl[0], err = sm.ctrl[1], cur_pos = sm.ctrl[2] - 1, P = sm.ctrl[3];
         if (fin || err) break;
-        const bool tracing = mp.trace != nullptr && step == mp.trace_step && cta == 0;
+        const bool tracing = TRACE && mp.trace != nullptr && step == mp.trace_step && cta == 0;
         for (int pi = 0; pi < mp.n_phases; ++pi) {
             const MegaPhase& ph = sm.phase[cur];
             MEGA_TRACE(0);
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
             if (ph.kind == 0) {
                 const int buf = g_idx & 1;
                 int r0, r1;
-                cta_rows(ph.g.N, cta, G, r0, r1);
+                cta_rows(ph.g.N, cta, ph.rpc, r0, r1);
                 // epilogue operands (bias, residual) of this warp's rows are requested first, together with the activations:
                 // lane j*NB + b holds them for the warp's j-th row and batch row b (no per-row register arrays -> one copy of the
                 // row code; the whole token loop has to stay inside the 32 KB L1.5 instruction cache)
@@ -213,11 +213,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                 // the top of the phase queued this phase's few small latency-critical loads (activations, LN affine, bias)
                 // behind it and cost ~2.5 us per phase.  It still has the rest of this phase plus the next prologue to land.
                 // issued by the LAST warp (it owns the fewest rows), from fields already in shared memory
-                if (tid == MEGA_THREADS - 32) prefetch_weights(ph.nx_W, ph.nx_ldw, ph.nx_N, ph.nx_K, sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, G);
+                if (tid == MEGA_THREADS - 32) prefetch_weights(ph.nx_W, ph.nx_ldw, ph.nx_N, ph.nx_K, sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, ph.nx_rpc);
                 wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, mp.error_flag);   // on a timeout the error flag ends the loop at the next token
                 MEGA_TRACE(3);
-                {
-                    int j = 0;
+                for (int rep = tracing ? 0 : 1; rep < 2; ++rep) {      // trace mode: a cold pass (stamp 12) and a warm one; idempotent, the
+                    int j = 0;                                          // residual operand was fetched before either pass stores
+                    if (rep == 1) MEGA_TRACE(12);
 #pragma unroll 1
                     for (int n = r0 + warp; n < r1; n += MEGA_WARPS, ++j) {
                         const bool pre = j < OPS_ROWS;
@@ -232,14 +233,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                 const int L = a.fixed_len > 0 ? a.fixed_len : cur_pos + 1;
                 const int units = a.rows * a.H * a.n_splits;
                 for (int u = cta; u < units; u += G) {
-                    const int s = u % a.n_splits, h = (u / a.n_splits) % a.H, r = u / (a.n_splits * a.H);
+                    // exact for u < 2^16 (units <= rows * H * n_splits, a few thousand at most)
+                    const int hr = ph.magic_ns ? (int)__umulhi((unsigned)u, ph.magic_ns) : u, s = u - hr * a.n_splits;      // magic 0: divisor 1
+                    const int r = ph.magic_h ? (int)__umulhi((unsigned)hr, ph.magic_h) : hr, h = hr - r * a.H;
                     decode_attention_body<MEGA_WARPS>(a, s, h, r, a.row_slot ? sm.ctrl[4 + r] : r, L, P, sm.u.attn.sc, sm.u.attn.red,
-                                                      sm.u.attn.stat, tid);
+                                                      sm.u.attn.stat, tid, tracing ? &mp.trace[(long long)pi * MEGA_TRACE_SLOTS + 6] : nullptr);
                     __syncthreads();
                 }
             } else {
                 if (cta < sm.sample_params.cfg->B) sample_body(sm.sample_params, cta, sm.u.sample);
             }
+            MEGA_TRACE(11);
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
             MEGA_TRACE(4);
@@ -260,17 +264,20 @@ size_t mega_smem_bytes() { return sizeof(MegaSmem) + 128; }
 int launch_megakernel(const MegaParams& mp, int grid, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_bytes()));
-        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_bytes()));
         int per_sm = 0;
-        MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel<2>, MEGA_THREADS, mega_smem_bytes()));
+        MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel<2, true>, MEGA_THREADS, mega_smem_bytes()));
         MB_REQUIRE(per_sm >= 1, "megakernel does not fit on an SM");
         configured = true;
     }
     MB_REQUIRE(mp.sample.rows >= 1 && mp.sample.rows <= MEGA_NB_MAX, "megakernel handles 1 or 2 decoder rows");
     MegaParams p = mp;
     void* args[] = {&p};
-    const void* fn = mp.sample.rows == 1 ? (const void*)decode_megakernel<1> : (const void*)decode_megakernel<2>;
+    const void* fn = mp.trace ? (mp.sample.rows == 1 ? (const void*)decode_megakernel<1, true> : (const void*)decode_megakernel<2, true>)
+                              : (mp.sample.rows == 1 ? (const void*)decode_megakernel<1, false> : (const void*)decode_megakernel<2, false>);
     MB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(MEGA_THREADS), args, mega_smem_bytes(), stream));
     ++g_launch_count;
     return 0;

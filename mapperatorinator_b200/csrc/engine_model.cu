@@ -528,6 +528,9 @@ static SampleParams sample_params(mb200_model* m, int rows) {
     return s;
 }
 
+// split-KV layout of the self-attention cache: one 128-key split while the context fits, 64-key splits beyond
+static int self_splits(int max_length) { return max_length <= 128 ? 1 : (max_length + 63) / 64; }
+
 // Either launches the 98 micro-phases of one token on `st` (eager / graph capture), or — when `collect` is given — records
 // them as phase descriptors for the persistent megakernel.  One definition, so both paths run the same arithmetic.
 static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaStream_t st, bool pdl,
@@ -539,7 +542,10 @@ static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaSt
     };
     auto emit_attn = [&](const DecAttnParams& a) -> int {
         if (!collect) return launch_decode_attention(a, st, pdl);
-        MegaPhase ph{}; ph.kind = 1; ph.a = a; collect->push_back(ph);
+        MegaPhase ph{}; ph.kind = 1; ph.a = a;
+        ph.magic_ns = a.n_splits > 1 ? (unsigned)((1ull << 32) / (unsigned)a.n_splits + 1) : 0u;       // 0 = divisor 1 (2^32 + 1 does not fit)
+        ph.magic_h = a.H > 1 ? (unsigned)((1ull << 32) / (unsigned)a.H + 1) : 0u;
+        collect->push_back(ph);
         return 0;
     };
     const auto& c = m->cfg;
@@ -567,7 +573,8 @@ static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaSt
             DecAttnParams a{};
             a.q = q; a.q_ld = d; a.kc = skv; a.vc = skv + d; a.row_stride = self_row; a.tok_stride = 2 * d; a.row_slot = nullptr;
             a.fixed_len = 0; a.st = gs; a.key_valid = m->g_keyvalid.as<unsigned char>(); a.key_valid_ld = c.tgt_seq_len;
-            a.part_o = po; a.part_ml = pml; a.rows = rows; a.H = H; a.n_splits = n_splits_self; a.chunk = chunk;
+            a.part_o = po; a.part_ml = pml; a.rows = rows; a.H = H; a.n_splits = n_splits_self;
+            a.chunk = n_splits_self == 1 ? 128 : chunk;      // contexts up to 128 tokens: one split per head, no merge step
             a.out = attn; a.out_ld = d; a.ticket = ticket;
             MB_TRY(emit_attn(a));
         }
@@ -620,6 +627,8 @@ static int token_step(mb200_model* m, int rows, int B, int n_splits_self, cudaSt
             (*collect)[i].next_gemv = j;
             (*collect)[i].nx_W = (*collect)[j].g.W; (*collect)[i].nx_ldw = (*collect)[j].g.ldw;
             (*collect)[i].nx_N = (*collect)[j].g.N; (*collect)[i].nx_K = (*collect)[j].g.K;
+            (*collect)[i].nx_rpc = ((*collect)[j].g.N + m->num_sms - 1) / m->num_sms;
+            (*collect)[i].rpc = (*collect)[i].kind == 0 ? ((*collect)[i].g.N + m->num_sms - 1) / m->num_sms : 0;
         }
         return 0;
     }
@@ -737,7 +746,7 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
 
     // partial buffers for the split-KV attentions
     const int chunk = 64;
-    const int n_splits_self = (gp->max_length + chunk - 1) / chunk;
+    const int n_splits_self = self_splits(gp->max_length);
     (void)H; (void)T;
 
     MB_TRY(launch_prompt_scan(m->g_ids.as<long long>(), ids_ld, B, P, m->g_vflags.as<unsigned char>(), sc.ts_start, sc.ts_end,
@@ -883,7 +892,7 @@ extern "C" int mb200_model_set_option(mb200_model* m, const char* name, int valu
     }
     if (!strcmp(name, "mega")) { m->use_mega = value != 0; return 0; }
     if (!strcmp(name, "mega_trace")) {
-        if (value) { MB_TRY(m->mega_trace.ensure(128 * 12 * 8)); MB_CUDA_CHECK(cudaMemset(m->mega_trace.p, 0, 128 * 12 * 8)); }
+        if (value) { MB_TRY(m->mega_trace.ensure(128 * 16 * 8)); MB_CUDA_CHECK(cudaMemset(m->mega_trace.p, 0, 128 * 16 * 8)); }
         return 0;
     }
     set_last_error(std::string("unknown option ") + name);
@@ -902,7 +911,7 @@ extern "C" int mb200_model_profile_step(mb200_model* m, int32_t rows, int32_t B,
     const int cur0 = gs.prompt_len + 1;
     double acc[3] = {0, 0, 0}; long long cnt[3] = {0, 0, 0};
     if (!g_prof.created) { for (auto& e : g_prof.ev) MB_CUDA_CHECK(cudaEventCreate(&e)); g_prof.created = true; }
-    const int n_splits_self = (max_length + 63) / 64;
+    const int n_splits_self = self_splits(max_length);
     for (int it = 0; it < iters; ++it) {
         gs.cur_len = cur0 + it; gs.all_finished = 0; gs.n_finished = 0; gs.ticket = 0; gs.max_length = m->cfg.tgt_seq_len; gs.min_new_tokens = 0;
         MB_CUDA_CHECK(cudaMemcpy(m->g_state.p, &gs, sizeof(gs), cudaMemcpyHostToDevice));
@@ -923,11 +932,11 @@ extern "C" int mb200_model_profile_step(mb200_model* m, int32_t rows, int32_t B,
     return 0;
 }
 
-// debug: copy the megakernel phase trace (option "mega_trace") to host: out[n_phases][12] SM-cycle stamps
+// debug: copy the megakernel phase trace (option "mega_trace") to host: out[n_phases][16] SM-cycle stamps
 extern "C" int mb200_model_read_trace(mb200_model* m, uint64_t* out, int32_t n_phases) {
     MB_REQUIRE(m && out && m->mega_trace.p && n_phases <= 128, "trace not enabled");
     MB_CUDA_CHECK(cudaDeviceSynchronize());
-    MB_CUDA_CHECK(cudaMemcpy(out, m->mega_trace.p, (size_t)n_phases * 12 * 8, cudaMemcpyDeviceToHost));
+    MB_CUDA_CHECK(cudaMemcpy(out, m->mega_trace.p, (size_t)n_phases * 16 * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -178,6 +178,8 @@ struct MegaPhase {                            // one dependent micro-phase of a 
     int kind;                                 // 0 GEMV, 1 split-KV attention, 2 logits chain + token selection
     int next_gemv;                            // index of the next GEMV phase (wraps into the next token)
     const float* nx_W; long long nx_ldw; int nx_N, nx_K;   // its weight matrix, so the prefetch needs no extra global reads
+    unsigned magic_ns, magic_h;               // floor(2^32 / d) + 1 for d = n_splits, H (0 when d == 1): unit -> (split, head, row) without integer division
+    int rpc, nx_rpc;                          // output rows per CTA of this / the next GEMV phase (ceil(N / grid), host-computed)
     GemvParams g;
     DecAttnParams a;
 };

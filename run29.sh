@@ -1,0 +1,1 @@
+timeout 300 python tools/mega_trace.py 2>&1 | tail -12

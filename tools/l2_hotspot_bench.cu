@@ -21,12 +21,20 @@ constexpr int K = 768, R = 8, THREADS = 512, WB = 64 * 1024;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned target) {
+// NC arrival counters (64 words apart: different L2 lines/slices); CTA c arrives on counter c % NC, lanes 0..NC-1 of warp 0 poll one each
+__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned round, int nc) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-        unsigned v = 0;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x, G = gridDim.x;
+        if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter + (blockIdx.x % nc) * 64) : "memory");
+        const unsigned per = lane < nc ? (unsigned)((G - lane + nc - 1) / nc) : 0u;      // CTAs that arrive on this lane's counter
+        const unsigned target = per * round;
+        bool ok;
+        do {
+            unsigned v = target;
+            if (lane < nc) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter + lane * 64) : "memory");
+            ok = __all_sync(0xffffffffu, v >= target);
+        } while (!ok);
     }
     __syncthreads();
 }
@@ -39,7 +47,7 @@ struct Params {
     long long* lat;      // [grid] summed cycles
     long long* bar;      // [grid] summed barrier cycles
     float* sink;
-    int mode, stream, iters;
+    int mode, stream, iters, nc;
 };
 
 __global__ void __launch_bounds__(THREADS, 1) bench_kernel(Params p) {
@@ -51,7 +59,7 @@ __global__ void __launch_bounds__(THREADS, 1) bench_kernel(Params p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    unsigned target = 0;
+    unsigned round = 0;
     long long lat = 0, bar = 0;
     float acc = 0.f;
     size_t woff = (size_t)cta * (WB / 4);
@@ -73,8 +81,7 @@ __global__ void __launch_bounds__(THREADS, 1) bench_kernel(Params p) {
             if (woff + WB / 4 > p.weight_floats) woff = (size_t)cta * (WB / 4);
         }
         long long t0 = clock64();
-        target += G;
-        grid_sync(p.counter, target);
+        grid_sync(p.counter, ++round, p.nc);
         long long t1 = clock64();
         if (tid < 32) {
             const float* src = p.mode == 0 ? p.x : p.mode == 1 ? p.x + (cta % R) * K : p.mode == 2 ? p.x : p.priv + (size_t)cta * K;
@@ -94,8 +101,7 @@ __global__ void __launch_bounds__(THREADS, 1) bench_kernel(Params p) {
             while (!ok) asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
                                      : "=r"(ok) : "r"(smem_u32(&mbar)), "r"(it & 1) : "memory");
         }
-        target += G;
-        grid_sync(p.counter, target);          // readers done before the next overwrite
+        grid_sync(p.counter, ++round, p.nc);          // readers done before the next overwrite
     }
     if (tid == 0) { p.lat[cta] = lat; p.bar[cta] = bar; }
     if (tid < 32) p.sink[cta * 32 + lane] = acc;
@@ -112,13 +118,13 @@ int main() {
     CK(cudaMalloc(&x, R * K * 4)); CK(cudaMemset(x, 0, R * K * 4));
     CK(cudaMalloc(&priv, (size_t)G * K * 4)); CK(cudaMemset(priv, 0, (size_t)G * K * 4));
     CK(cudaMalloc(&weights, wfloats * 4)); CK(cudaMemset(weights, 0, wfloats * 4));
-    CK(cudaMalloc(&sink, G * 32 * 4)); CK(cudaMalloc(&counter, 4)); CK(cudaMalloc(&lat, G * 8)); CK(cudaMalloc(&bar, G * 8));
+    CK(cudaMalloc(&sink, G * 32 * 4)); CK(cudaMalloc(&counter, 64 * 64 * 4)); CK(cudaMalloc(&lat, G * 8)); CK(cudaMalloc(&bar, G * 8));
     CK(cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WB));
     const char* names[4] = {"same vector, freshly written", "8 replicas, freshly written", "same vector, clean", "private vector per CTA"};
     for (int stream = 0; stream < 2; ++stream)
         for (int mode = 0; mode < 4; ++mode) {
-            CK(cudaMemset(counter, 0, 4));
-            Params p{x, priv, weights, wfloats, counter, lat, bar, sink, mode, stream, iters};
+            CK(cudaMemset(counter, 0, 64 * 64 * 4));
+            Params p{x, priv, weights, wfloats, counter, lat, bar, sink, mode, stream, iters, 1};
             void* args[] = {&p};
             cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
             CK(cudaEventRecord(e0));
@@ -133,5 +139,20 @@ int main() {
             printf("stream=%d mode=%d (%-30s): load round trip mean %7.0f cyc, slowest CTA %7.0f cyc; barrier %7.0f cyc; %.2f us / iteration\n", stream, mode,
                    names[mode], sl / G / iters, mx / iters, sb / G / iters, 1000.0 * ms / iters);
         }
+    for (int nc : {1, 2, 4, 8, 16, 32}) {          // barrier cost vs number of arrival counters (mode 3: private loads, no stream)
+        CK(cudaMemset(counter, 0, 64 * 64 * 4));
+        Params p{x, priv, weights, wfloats, counter, lat, bar, sink, 3, 0, iters, nc};
+        void* args[] = {&p};
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0));
+        CK(cudaLaunchCooperativeKernel((const void*)bench_kernel, dim3(G), dim3(THREADS), args, WB, 0));
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        std::vector<long long> hb(G);
+        CK(cudaMemcpy(hb.data(), bar, G * 8, cudaMemcpyDeviceToHost));
+        double sb = 0; for (int i = 0; i < G; ++i) sb += hb[i];
+        printf("barrier with %2d arrival counters: %7.0f cyc mean per barrier; %.2f us / iteration (2 barriers + 1 load round trip)\n", nc, sb / G / iters, 1000.0 * ms / iters);
+    }
     return 0;
 }
