@@ -225,6 +225,21 @@ __global__ void __launch_bounds__(128) gemm_skinny_kernel(GemmParams p) {
 
 }  // namespace
 
+// fixed-size split-K workspace, allocated once (captured graphs hold this pointer); null if `need` does not fit
+float* splitk_workspace(size_t need) {
+    static float* ws = nullptr;
+    static const size_t ws_bytes = (size_t)64 << 20;
+    if (!ws && cudaMalloc(&ws, ws_bytes) != cudaSuccess) { ws = nullptr; return nullptr; }
+    return need <= ws_bytes ? ws : nullptr;
+}
+
+int launch_splitk_reduce(const GemmParams& q, cudaStream_t stream) {
+    gemm_splitk_reduce_kernel<<<(unsigned)(((long long)q.M * q.N + 255) / 256), 256, 0, stream>>>(q);
+    MB_LAUNCH_CHECK();
+    ++g_launch_count;
+    return 0;
+}
+
 int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     MB_REQUIRE(p.K % 4 == 0, "GEMM K must be a multiple of 4 (float4 loads)");
     MB_REQUIRE(p.A.ld % 4 == 0 && p.ldw % 4 == 0, "GEMM operand row strides must be multiples of 4 floats");
@@ -243,26 +258,18 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     if ((long long)tiles_m * tiles_n < 100 && small_m_mode == 2 && p.K >= 64) {
         // fewer output tiles than SMs (decoder prefill, a single encoder window, DiT conditioning): split K over enough CTAs to
         // fill the machine — these problems are weight-streaming bound, not FLOP bound
-        static float* ws = nullptr;
-        static size_t ws_bytes = 0;
         const int tiles = tiles_m * tiles_n;
         int splits = std::max(1, std::min((148 + tiles - 1) / tiles, p.K / 32));
         const int kps = ((p.K + splits - 1) / splits + BK - 1) / BK * BK;
         splits = (p.K + kps - 1) / kps;
-        const size_t need = (size_t)splits * p.M * p.N * sizeof(float);
-        if (!ws) {   // fixed-size workspace, allocated once: captured graphs hold this pointer
-            ws_bytes = (size_t)64 << 20;
-            MB_CUDA_CHECK(cudaMalloc(&ws, ws_bytes));
-        }
-        if (splits > 1 && need <= ws_bytes) {
+        float* ws = splits > 1 ? splitk_workspace((size_t)splits * p.M * p.N * sizeof(float)) : nullptr;
+        if (ws) {
             GemmParams q = p;
             q.splitk_ws = ws; q.splitk = splits; q.k_per_split = kps;
             gemm_f32_kernel<<<dim3(tiles_n, tiles_m, splits), 256, 0, stream>>>(q);
             MB_LAUNCH_CHECK();
-            gemm_splitk_reduce_kernel<<<(unsigned)(((long long)p.M * p.N + 255) / 256), 256, 0, stream>>>(q);
-            MB_LAUNCH_CHECK();
-            g_launch_count += 2;
-            return 0;
+            ++g_launch_count;
+            return launch_splitk_reduce(q, stream);
         }
     }
     dim3 grid((p.N + BN - 1) / BN, (unsigned)((p.M + BM - 1) / BM));

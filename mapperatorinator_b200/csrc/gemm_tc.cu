@@ -9,8 +9,10 @@
 //   warp 0 / lane 0 : TMA producer — 4 tiles per k-block (A, Alo, W, Wlo; 128 rows x 32 floats, SWIZZLE_128B) into a 3-stage ring
 //   warp 1 / lane 0 : MMA issuer   — 12 x tcgen05.mma (128x128x8) per k-block into a 128-column fp32 TMEM accumulator,
 //                     tcgen05.commit frees the stage / publishes the accumulator
-//   warps 2..5      : epilogue     — tcgen05.ld (32 lanes x 32 columns per warp and pass) -> bias / activation / gate /
-//                     residual (same GemmParams epilogue as gemm.cu) -> global
+//   warps 2..5      : epilogue     — tcgen05.ld (32 lanes x 32 columns per warp and pass) -> per-warp shared-memory transpose ->
+//                     bias / activation / gate / residual (same GemmParams epilogue as gemm.cu) -> 128-byte coalesced stores
+// Measured alternative (kept out): deriving hi/lo inside the kernel from raw tiles (half the L2->SM operand traffic, no mirror
+// copies) was 10-15 % SLOWER — the split's shared-memory traffic competes with the MMA's own operand reads.
 // A may be any RowMap (im2col-free conv over the padded buffer, batched rows) via a 3-D tensor map.
 // Every wait is bounded: on a timeout the kernel sets an error flag and falls through, it can never hang the GPU.
 #include <cuda.h>
@@ -88,7 +90,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * TC_BN;
     const long long m0 = (long long)blockIdx.y * TC_BM;
-    const int nkb = (p.K + TC_BK - 1) / TC_BK;
+    const int nkb_all = (p.K + TC_BK - 1) / TC_BK;
+    // split-K (under-filled grids): CTA z owns k-blocks [kb0, kb0 + nkb) and stores raw partial sums; gemm.cu's reduce kernel finishes
+    const int kb0 = p.splitk > 1 ? blockIdx.z * (p.k_per_split / TC_BK) : 0;
+    const int nkb = p.splitk > 1 ? max(0, min(nkb_all - kb0, p.k_per_split / TC_BK)) : nkb_all;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -118,7 +123,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 unsigned char* st = smem + s * TC_STAGE_BYTES;
                 const unsigned fb = s32(&bars->full[s]);
                 asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(fb), "r"(TC_STAGE_BYTES) : "memory");
-                const int k0 = kb * TC_BK;
+                const int k0 = (kb0 + kb) * TC_BK;
                 asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                              ::"r"(s32(st)), "l"(&map_a), "r"(k0), "r"(a_t), "r"(a_b), "r"(fb) : "memory");
                 asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -158,15 +163,29 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const bool ok = bar_wait(&bars->tmem_full, 0, err);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;                          // TMEM lane group this warp may access
-        const long long m = m0 + lg * 32 + lane;
-        float* crow = nullptr;
-        const float* rrow = nullptr;
-        const float* grow = nullptr;
-        if (ok && m < p.M) {
-            crow = p.C.row(m);
-            rrow = p.R.ptr ? p.R.row(m) : nullptr;
-            grow = p.gate ? p.gate + (m / p.gate_rpb) * p.gate_ld : nullptr;
+        // Epilogue: tcgen05.ld hands every thread 32 consecutive columns of ITS row, so storing straight from registers would make
+        // each store instruction touch 32 different rows (32 sectors per instruction; measured: the epilogue, not the MMA pipe,
+        // set the kernel's duration).  Each warp transposes its 32x32 block through shared memory instead (the pipeline stages
+        // are idle by now: every TMA load and every MMA that reads them completed before tmem_full fired) and then walks the
+        // block row by row with lane = column: bias / gate / residual loads and the C store are all 128-byte coalesced.
+        float* stg = reinterpret_cast<float*>(smem) + lg * (32 * 33);                    // [32 rows][33] per warp
+        struct RowPtrs { float* c; const float* r; const float* g; };
+        RowPtrs* rows = reinterpret_cast<RowPtrs*>(smem + 4 * 32 * 33 * 4) + lg * 32;  // this warp's 32 row bases
+        {
+            const long long m = m0 + lg * 32 + lane;
+            RowPtrs rp{nullptr, nullptr, nullptr};
+            if (ok && m < p.M) {
+                if (p.splitk > 1) {
+                    rp.c = p.splitk_ws + ((long long)blockIdx.z * p.M + m) * p.N;         // raw partial sums of this split
+                } else {
+                    rp.c = p.C.row(m);
+                    rp.r = p.R.ptr ? p.R.row(m) : nullptr;
+                    rp.g = p.gate ? p.gate + (m / p.gate_rpb) * p.gate_ld : nullptr;
+                }
+            }
+            rows[lane] = rp;
         }
+        __syncwarp();
 #pragma unroll 1
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
             unsigned v[32];
@@ -180,20 +199,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (crow) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < p.N) {
-                        float x = __uint_as_float(v[j]);
-                        if (p.bias) x += __ldg(p.bias + n);
-                        x = apply_act(x, p.act) * p.alpha;
-                        if (grow) x *= __ldg(grow + n);
-                        if (rrow) x += rrow[n];
-                        crow[n] = x;
-                    }
+            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);     // bank (lane + j) % 32: conflict-free
+            __syncwarp();
+            const int n = n0 + c0 + lane;
+            const bool n_ok = n < p.N;
+            const float bias_v = (n_ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+                const RowPtrs rp = rows[rr];                                              // broadcast
+                if (rp.c && n_ok) {
+                    float x = stg[rr * 33 + lane];
+                    if (p.splitk > 1) { rp.c[n] = x; continue; }
+                    if (p.bias) x += bias_v;
+                    x = apply_act(x, p.act) * p.alpha;
+                    if (rp.g) x *= __ldg(rp.g + n);
+                    if (rp.r) x += rp.r[n];
+                    rp.c[n] = x;
                 }
             }
+            __syncwarp();                                                                 // block consumed before the next chunk overwrites it
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -337,6 +362,24 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
         configured = true;
     }
     dim3 grid((p.N + TC_BN - 1) / TC_BN, (unsigned)((p.M + TC_BM - 1) / TC_BM));
+    // Under-filled grids (a single encoder window: 24-72 tiles on 148 SMs) split K so every SM gets a tile; each split keeps at
+    // least 8 k-blocks.  Fixed split -> fixed summation order.
+    const int tiles = (int)(grid.x * grid.y), nkb = (p.K + TC_BK - 1) / TC_BK;
+    int splits = std::min({4, 148 / std::max(1, tiles), nkb / 8});
+    if (splits > 1) {
+        const int kpb = (nkb + splits - 1) / splits;                  // k-blocks per split
+        splits = (nkb + kpb - 1) / kpb;                               // no empty split
+        float* ws = splits > 1 ? splitk_workspace((size_t)splits * p.M * p.N * sizeof(float)) : nullptr;
+        if (ws) {
+            GemmParams q = p;
+            q.splitk_ws = ws; q.splitk = splits; q.k_per_split = kpb * TC_BK;
+            grid.z = splits;
+            gemm_tf32x3_kernel<<<grid, TC_THREADS, smem, stream>>>(ma, mal, mw, mwl, q, p.A.rpb, g_tc_err);
+            MB_LAUNCH_CHECK();
+            g_launch_count += 2;
+            return launch_splitk_reduce(q, stream);
+        }
+    }
     gemm_tf32x3_kernel<<<grid, TC_THREADS, smem, stream>>>(ma, mal, mw, mwl, p, p.A.rpb, g_tc_err);
     MB_LAUNCH_CHECK();
     g_launch_count += 2;

@@ -26,6 +26,8 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream);
 // gemm_tc.cu — tcgen05 3xTF32 path (fp32-grade accuracy on the tensor cores); launch_gemm dispatches to it for large problems
 // whose weight matrix has a registered tf32 "lo" mirror
 extern int g_tc_enabled;
+float* splitk_workspace(size_t need);                       // gemm.cu: shared fixed-size split-K workspace (null if it does not fit)
+int launch_splitk_reduce(const GemmParams& q, cudaStream_t stream);
 bool tc_gemm_eligible(const GemmParams& p);
 int launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
 int tc_register_weight(const float* w, long long numel);
