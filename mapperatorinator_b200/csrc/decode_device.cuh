@@ -125,9 +125,11 @@ __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float
     const int K = p.K, K4 = K >> 2;
     const float4* wrow = reinterpret_cast<const float4*>(wrow_f);
     if (!have_operands) gemv_row_operands<NB>(p, n, b0, lane, bias_v, r_v);
-    float acc[NB];
+    // four independent accumulation chains per batch row (the x / y / z / w components of the float4 stream) instead of one
+    // 4*K/128-deep dependent FMA chain; merged as (x + y) + (z + w) before the shuffle tree
+    float4 acc[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+    for (int b = 0; b < NB; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr int U = W_GLOBAL ? 12 : 6;     // float4 loads in flight per lane (same j-major summation order either way)
     for (int base = 0; base < K4; base += 32 * U) {
         float4 w[U];
@@ -144,8 +146,8 @@ __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     float4 xv = reinterpret_cast<const float4*>(xs + b * K)[idx];
-                    acc[b] = fmaf(w[j].x, xv.x, acc[b]); acc[b] = fmaf(w[j].y, xv.y, acc[b]);
-                    acc[b] = fmaf(w[j].z, xv.z, acc[b]); acc[b] = fmaf(w[j].w, xv.w, acc[b]);
+                    acc[b].x = fmaf(w[j].x, xv.x, acc[b].x); acc[b].y = fmaf(w[j].y, xv.y, acc[b].y);
+                    acc[b].z = fmaf(w[j].z, xv.z, acc[b].z); acc[b].w = fmaf(w[j].w, xv.w, acc[b].w);
                 }
             }
         }
@@ -153,7 +155,7 @@ __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float
     float mine = 0.f;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        float s = warp_sum(acc[b]);
+        float s = warp_sum((acc[b].x + acc[b].y) + (acc[b].z + acc[b].w));
         if (lane == b) mine = s;
     }
     if (lane < NB && b0 + lane < p.B) {
