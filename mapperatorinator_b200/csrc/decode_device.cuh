@@ -121,10 +121,19 @@ __device__ __forceinline__ void gemv_row_operands(const GemvParams& p, int n, in
 
 template <int NB, bool W_GLOBAL>
 __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float* wrow_f, const float* xs, int b0, int lane, int cur_pos,
-                                         bool have_operands = false, float bias_v = 0.f, float r_v = 0.f) {
+                                         bool have_operands = false, float bias_v = 0.f, float r_v = 0.f, unsigned long long* dbg = nullptr) {
     const int K = p.K, K4 = K >> 2;
     const float4* wrow = reinterpret_cast<const float4*>(wrow_f);
     if (!have_operands) gemv_row_operands<NB>(p, n, b0, lane, bias_v, r_v);
+    // Everything the epilogue needs besides the dot product is derived NOW, branch-free and for every lane (batch index clamped), so
+    // its shared-memory lookups overlap the dot product instead of forming a ~0.25 us dependent chain behind the shuffle tree.
+    const int bl = min(b0 + (lane < NB ? lane : 0), p.B - 1);
+    const int si = (int)(p.nseg > 1 && n >= p.seg[1].n_begin) + (int)(p.nseg > 2 && n >= p.seg[2].n_begin);
+    const GemvSeg& sg = p.seg[si];
+    float* const outp = sg.out + ((long long)bl * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin));
+    const int act = sg.act;
+    const float alpha = sg.alpha;
+    const bool has_bias = p.bias != nullptr, has_res = p.R != nullptr;
     // four independent accumulation chains per batch row (the x / y / z / w components of the float4 stream) instead of one
     // 4*K/128-deep dependent FMA chain; merged as (x + y) + (z + w) before the shuffle tree
     float4 acc[NB];
@@ -152,22 +161,20 @@ __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float
             }
         }
     }
+    if (dbg && lane == 0) dbg[0] = (unsigned long long)clock64();
     float mine = 0.f;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         float s = warp_sum((acc[b].x + acc[b].y) + (acc[b].z + acc[b].w));
         if (lane == b) mine = s;
     }
+    if (dbg && lane == 0) dbg[1] = (unsigned long long)clock64();
     if (lane < NB && b0 + lane < p.B) {
-        const int b = b0 + lane;
-        int si = 0;
-        for (int s = 1; s < p.nseg; ++s) if (n >= p.seg[s].n_begin) si = s;
-        const GemvSeg& sg = p.seg[si];
         float v = mine;
-        if (p.bias) v += bias_v;
-        v = apply_act(v, sg.act) * sg.alpha;
-        if (p.R) v += r_v;
-        sg.out[(long long)b * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin)] = v;
+        if (has_bias) v += bias_v;
+        v = apply_act(v, act) * alpha;
+        if (has_res) v += r_v;
+        *outp = v;
     }
 }
 

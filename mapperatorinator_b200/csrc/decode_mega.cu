@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                         const bool pre = j < OPS_ROWS;
                         const float bias_v = __shfl_sync(0xffffffffu, bias_pref, (j * MEGA_NB) & 31);
                         const float r_v = __shfl_sync(0xffffffffu, r_pref, (j * MEGA_NB + (lane < MEGA_NB ? lane : 0)) & 31);
-                        gemv_row<MEGA_NB, false>(ph.g, n, sm.wbuf[buf] + (long long)(n - r0) * ph.g.K, sm.u.xs, 0, lane, cur_pos, pre, bias_v, r_v);
+                        gemv_row<MEGA_NB, false>(ph.g, n, sm.wbuf[buf] + (long long)(n - r0) * ph.g.K, sm.u.xs, 0, lane, cur_pos, pre, bias_v, r_v,
+                                                 (tracing && warp == 0 && rep == 1 && j == 0) ? &mp.trace[(long long)pi * MEGA_TRACE_SLOTS + 13] : nullptr);
                     }
                 }
                 ++g_idx;

@@ -30,7 +30,7 @@ names = ["qkv", "self_attn", "out", "q_c", "cross_attn", "out_c", "fc1", "fc2"]
 tot = t[-1, 5] - t[0, 0]
 print(f"token total {tot / 1e3:.1f} us over {n} phases")
 print("phase            own_stage (issue, loads, rest)  sync   pref+wait   math   barrier    total (us)")
-agg, warm, own, attn = {}, {}, {}, {}
+agg, warm, own, attn, rowt = {}, {}, {}, {}, {}
 for i in range(n):
     nm = names[i % 8] if i < 96 else ("proj_out" if i == 96 else "sample")
     s0, s1, s2, s3, s4, s5 = (t[i, j] for j in range(6))
@@ -46,10 +46,12 @@ for i in range(n):
         warm.setdefault(nm, []).append(((s7 - s6) if s7 > 0 else 0, (s1 - s7) if s7 > 0 else s1 - s6))
         seg = (c2 - s0,) + ld + (s2 - s1, s3 - s2, s4 - s3, s5 - s4)
         own.setdefault(nm, []).append((t[i, 12] - s3, t[i, 11] - t[i, 12]))
+        rowt.setdefault(nm, []).append((t[i, 13] - t[i, 12], t[i, 14] - t[i, 13], t[i, 11] - t[i, 14]))
     agg.setdefault(nm, []).append(seg + (s5 - s0,))
 for nm, v in agg.items():
     a = np.array(v, dtype=np.float64).mean(0) / 1e3
     print(f"{nm:12s} x{len(v):3d} {a[0]:8.2f} ({a[1]:5.2f} {a[2]:5.2f} {a[3]:5.2f}) {a[4]:8.2f} {a[5]:8.2f} {a[6]:7.2f} {a[7]:9.2f} {a[8]:8.2f}"
           + f"   warp 0's rows cold {np.mean([o[0] for o in own[nm]]) / 1e3:.2f} warm {np.mean([o[1] for o in own[nm]]) / 1e3:.2f}"
           + (f"   [K/V loaded+scores {np.mean([x[0] for x in attn[nm]]) / 1e3:.2f} softmax {np.mean([x[1] for x in attn[nm]]) / 1e3:.2f} PV+partials {np.mean([x[2] for x in attn[nm]]) / 1e3:.2f} ticket(+merge) {np.mean([x[3] for x in attn[nm]]) / 1e3:.2f}]" if nm in attn else "")
+          + (f"   first row (warm): dot {np.mean([x[0] for x in rowt[nm]]) / 1e3:.2f} shuffle-sum {np.mean([x[1] for x in rowt[nm]]) / 1e3:.2f} epilogue(+more rows) {np.mean([x[2] for x in rowt[nm]]) / 1e3:.2f}" if nm in rowt else "")
           + (f"   warm re-run of the staging: loads {np.mean([w[0] for w in warm[nm]]) / 1e3:.2f} rest {np.mean([w[1] for w in warm[nm]]) / 1e3:.2f}" if nm in warm else ""))
