@@ -106,12 +106,15 @@ __device__ __forceinline__ unsigned long long gtimer() {
         if (tracing && tid == 0) mp.trace[(long long)pi * MEGA_TRACE_SLOTS + (slot)] = gtimer();                     \
     } while (0)
 
-__device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int target, int* error_flag) {
-    // arrive = one fire-and-forget release reduction (cumulative over the CTA's writes through the bar.sync before it);
-    // wait = acquire polling.  One L2 round trip after the last arrival, no separate fences.
-    __syncthreads();
+// Grid barrier, split in two so that work which does not depend on other CTAs (the next phase's row range, its bias prefetch) runs
+// between the arrival and the wait instead of behind the barrier.
+// arrive = one fire-and-forget release reduction (cumulative over the CTA's writes through the bar.sync before it);
+// wait = acquire polling by thread 0.  One L2 round trip after the last arrival, no separate fences.
+__device__ __forceinline__ void grid_arrive(unsigned int* counter) {
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int target, int* error_flag) {
     if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned int v = 0;
         long long spin = 0;
         while (true) {
@@ -158,6 +161,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
     int cur = 0;
     load_desc(0, 0);
     __syncthreads();
+    // Prologue of a GEMV phase that needs nothing from other CTAs: this CTA's row range and the bias of this warp's rows (lane
+    // j*NB + b holds it for the warp's j-th row).  Computed between the previous barrier's arrival and its wait.
+    int pre_r0 = 0, pre_r1 = 0;
+    float pre_bias = 0.f;
+    auto gemv_prologue = [&](const MegaPhase& nx) {
+        if (nx.kind != 0) return;
+        cta_rows(nx.g.N, cta, nx.rpc, pre_r0, pre_r1);
+        pre_bias = 0.f;
+        const int n = pre_r0 + warp + (lane / MEGA_NB) * MEGA_WARPS;
+        if (n < pre_r1 && nx.g.bias) pre_bias = __ldg(nx.g.bias + n);
+    };
+    gemv_prologue(sm.phase[0]);
 
     for (int step = 0; step < mp.max_steps; ++step) {
         // uniform across the grid: all three were written before the previous grid barrier
@@ -184,20 +199,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
             }
             if (ph.kind == 0) {
                 const int buf = g_idx & 1;
-                int r0, r1;
-                cta_rows(ph.g.N, cta, ph.rpc, r0, r1);
-                // epilogue operands (bias, residual) of this warp's rows are requested first, together with the activations:
-                // lane j*NB + b holds them for the warp's j-th row and batch row b (no per-row register arrays -> one copy of the
-                // row code; the whole token loop has to stay inside the 32 KB L1.5 instruction cache)
+                const int r0 = pre_r0, r1 = pre_r1;
+                // epilogue operands of this warp's rows: lane j*NB + b holds them for the warp's j-th row and batch row b (no per-row
+                // register arrays -> one copy of the row code).  The bias came with the pre-barrier prologue; the residual is another
+                // CTA's output of the previous phase and is requested now, together with the activations.
                 constexpr int OPS_ROWS = 32 / MEGA_NB;
-                float bias_pref = 0.f, r_pref = 0.f;
+                const float bias_pref = pre_bias;
+                float r_pref = 0.f;
                 {
                     const int j = lane / MEGA_NB, b = lane - j * MEGA_NB;
                     const int n = r0 + warp + j * MEGA_WARPS;
-                    if (n < r1 && b < ph.g.B) {
-                        if (ph.g.bias) bias_pref = __ldg(ph.g.bias + n);
-                        if (ph.g.R) r_pref = __ldcg(ph.g.R + (long long)b * ph.g.r_ld + n);
-                    }
+                    if (n < r1 && b < ph.g.B && ph.g.R) r_pref = __ldcg(ph.g.R + (long long)b * ph.g.r_ld + n);
                 }
                 // trace mode runs the staging twice through the SAME code: pass 0 (slots 8, 9, 10) is what production pays, pass 1
                 // (slots 6, 7, 1) repeats it with instruction cache / TLB / L2 state warm — the difference is fetch, not data, latency
@@ -246,10 +258,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
             }
             MEGA_TRACE(11);
             asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncthreads();
+            __syncthreads();                              // this CTA's stores are done; the next descriptor has landed
             MEGA_TRACE(4);
             sync_target += G;
-            grid_sync(mp.sync_counter, sync_target, mp.error_flag);
+            grid_arrive(mp.sync_counter);
+            gemv_prologue(sm.phase[cur ^ 1]);
+            grid_wait(mp.sync_counter, sync_target, mp.error_flag);
             MEGA_TRACE(5);
             cur ^= 1;
         }
