@@ -43,7 +43,10 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(DecAttnParams p) 
     const int L = p.fixed_len > 0 ? p.fixed_len : p.st->cur_len;
     const int P = p.st ? p.st->prompt_len : 0;
     const int r = blockIdx.z;
-    decode_attention_body<4>(p, blockIdx.x, blockIdx.y, r, p.row_slot ? p.row_slot[r] : r, L, P, sc, red, stat, threadIdx.x);
+    const int slot = p.row_slot ? p.row_slot[r] : r;
+    AttnRegs<4> regs;
+    decode_attention_load<4>(p, blockIdx.x, blockIdx.y, r, slot, L, P, threadIdx.x, regs);
+    decode_attention_body<4>(p, blockIdx.x, blockIdx.y, r, slot, L, P, sc, red, stat, threadIdx.x, regs);
 }
 
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleParams p) {

@@ -242,10 +242,58 @@ __device__ __forceinline__ void decode_attention_merge(const DecAttnParams& p, i
 // ---------------------------------------------------------------------------------------------------------------------
 // split-KV decode attention for one (split s, head h, row r); NW warps cooperate; smem: sc[128], red[NW][64], stat[2]
 // ---------------------------------------------------------------------------------------------------------------------
+// K / validity / V operands of one (split, head, row) unit, held in registers between the load and the compute half so that the load
+// can be issued EARLY: cross-attention K/V are constants of the call, the megakernel requests them before the preceding grid barrier.
+template <int NW>
+struct AttnRegs {
+    static constexpr int SC_ITERS = 128 / (4 * NW), PV_PRE = 16;
+    float4 ka[SC_ITERS], kb4[SC_ITERS];
+    unsigned char kvalid[SC_ITERS];                      // prompt-padding validity, fetched in the same batch as K
+    float2 vpre[PV_PRE];
+};
+
+template <int NW>
+__device__ __forceinline__ void decode_attention_load(const DecAttnParams& p, int s, int h, int r, int slot, int L, int P, int tid, AttnRegs<NW>& R) {
+    constexpr int SC_ITERS = AttnRegs<NW>::SC_ITERS, PV_PRE = AttnRegs<NW>::PV_PRE;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
+    // one 64-bit base per operand, 32-bit offsets from there (token strides and chunk offsets are small)
+    const int tok = (int)p.tok_stride;
+    const float* kb = p.kc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
+    const float* vb = p.vc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
+    const unsigned char* kv = p.key_valid ? p.key_valid + (long long)r * p.key_valid_ld + k_begin : nullptr;
+    const int nk = k_end - k_begin, n_prompt = P - k_begin;      // keys [0, n_prompt) of this split are prompt positions (nk <= 0: empty split)
+    const int sub = lane & 7, kq = lane >> 3;                   // scores: 8 lanes per key, each lane owns 8 of the 64 dims
+    // fixed trip count (chunk <= 128) so every K load of the chunk is in flight before the first shuffle
+#pragma unroll
+    for (int it = 0; it < SC_ITERS; ++it) {
+        const int kk = it * 4 * NW + warp * 4 + kq;
+        R.kvalid[it] = 1;
+        if (kk < nk) {
+            const float* kr = kb + kk * tok + sub * 8;
+            R.ka[it] = ldcg4(kr); R.kb4[it] = ldcg4(kr + 4);
+            if (kv && kk < n_prompt) R.kvalid[it] = kv[kk];
+        } else {
+            R.ka[it] = make_float4(0, 0, 0, 0); R.kb4[it] = make_float4(0, 0, 0, 0);
+        }
+    }
+    // V rows do not depend on the scores: fetched in the same batch (warps 0..3, 16 keys each cover a 64-key chunk) so the whole
+    // phase costs one memory round trip instead of two
+    if (warp < 4) {
+#pragma unroll
+        for (int i = 0; i < PV_PRE; ++i) {
+            const int kk = warp + 4 * i;
+            R.vpre[i] = kk < nk ? ldcg2(vb + kk * tok + lane * 2) : make_float2(0.f, 0.f);
+        }
+    }
+}
+
 template <int NW>
 __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, int s, int h, int r, int slot, int L, int P, float* sc,
-                                                      float (*red)[64], float* stat, int tid, unsigned long long* dbg = nullptr) {
+                                                      float (*red)[64], float* stat, int tid, const AttnRegs<NW>& R,
+                                                      unsigned long long* dbg = nullptr) {
 #define ATTN_STAMP(i) do { if (dbg && tid == 0) dbg[i] = (unsigned long long)clock64(); } while (0)
+    constexpr int SC_ITERS = AttnRegs<NW>::SC_ITERS, PV_PRE = AttnRegs<NW>::PV_PRE;
     const int lane = tid & 31, warp = tid >> 5;
     const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
     const long long out_idx = ((long long)r * p.H + h) * p.n_splits + s;
@@ -253,44 +301,13 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
         if (p.n_splits == 1) { if (tid < 64) p.out[(long long)r * p.out_ld + h * 64 + tid] = 0.f; return; }
         if (tid == 0) { p.part_ml[out_idx * 2] = -INFINITY; p.part_ml[out_idx * 2 + 1] = 0.f; }
     } else {
-    // one 64-bit base per operand, 32-bit offsets from there (token strides and chunk offsets are small)
     const int tok = (int)p.tok_stride;
-    const float* kb = p.kc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
     const float* vb = p.vc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
-    const unsigned char* kv = p.key_valid ? p.key_valid + (long long)r * p.key_valid_ld + k_begin : nullptr;
-    const int nk = k_end - k_begin, n_prompt = P - k_begin;      // keys [0, n_prompt) of this split are prompt positions
-
-    // scores: 8 lanes per key, each lane owns 8 of the 64 dims
+    const int nk = k_end - k_begin;
     const int sub = lane & 7, kq = lane >> 3;
     const float* qp = p.q + (long long)r * p.q_ld + h * 64 + sub * 8;
-    const float4 q0 = ldcg4(qp), q1 = ldcg4(qp + 4);
-    // fixed trip count (chunk <= 128) so every K load of the chunk is in flight before the first shuffle
-    constexpr int SC_ITERS = 128 / (4 * NW);
-    float4 ka[SC_ITERS], kb4[SC_ITERS];
-    unsigned char kvalid[SC_ITERS];                      // prompt-padding validity, fetched in the same batch as K
-#pragma unroll
-    for (int it = 0; it < SC_ITERS; ++it) {
-        const int kk = it * 4 * NW + warp * 4 + kq;
-        kvalid[it] = 1;
-        if (kk < nk) {
-            const float* kr = kb + kk * tok + sub * 8;
-            ka[it] = ldcg4(kr); kb4[it] = ldcg4(kr + 4);
-            if (kv && kk < n_prompt) kvalid[it] = kv[kk];
-        } else {
-            ka[it] = make_float4(0, 0, 0, 0); kb4[it] = make_float4(0, 0, 0, 0);
-        }
-    }
-    // V rows do not depend on the scores: fetch them now (warps 0..3, 16 keys each cover a 64-key chunk) so the whole phase
-    // costs one memory round trip instead of two
-    constexpr int PV_PRE = 16;
-    float2 vpre[PV_PRE];
-    if (warp < 4) {
-#pragma unroll
-        for (int i = 0; i < PV_PRE; ++i) {
-            const int kk = warp + 4 * i;
-            vpre[i] = kk < nk ? ldcg2(vb + kk * tok + lane * 2) : make_float2(0.f, 0.f);
-        }
-    }
+    const float4 q0 = ldcg4(qp), q1 = ldcg4(qp + 4);      // the only operand another CTA produced in the previous phase
+    const auto& ka = R.ka; const auto& kb4 = R.kb4; const auto& kvalid = R.kvalid; const auto& vpre = R.vpre;
 #pragma unroll
     for (int it = 0; it < SC_ITERS; ++it) {
         const int kk = it * 4 * NW + warp * 4 + kq;

@@ -165,14 +165,33 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
     // j*NB + b holds it for the warp's j-th row).  Computed between the previous barrier's arrival and its wait.
     int pre_r0 = 0, pre_r1 = 0;
     float pre_bias = 0.f;
-    auto gemv_prologue = [&](const MegaPhase& nx) {
-        if (nx.kind != 0) return;
-        cta_rows(nx.g.N, cta, nx.rpc, pre_r0, pre_r1);
-        pre_bias = 0.f;
-        const int n = pre_r0 + warp + (lane / MEGA_NB) * MEGA_WARPS;
-        if (n < pre_r1 && nx.g.bias) pre_bias = __ldg(nx.g.bias + n);
+    // ... and of a cross-attention phase: its K/V are constants of the call (encoder states), so this CTA's first unit requests
+    // them before the barrier; after it only q (the previous phase's output) is still to come.
+    AttnRegs<MEGA_WARPS> areg;
+    bool areg_valid = false;
+    auto unit_of = [&](const MegaPhase& ph_, int u, int& s_, int& h_, int& r_) {      // exact for u < 2^16 (magic 0: divisor 1)
+        const int hr = ph_.magic_ns ? (int)__umulhi((unsigned)u, ph_.magic_ns) : u;
+        s_ = u - hr * ph_.a.n_splits;
+        r_ = ph_.magic_h ? (int)__umulhi((unsigned)hr, ph_.magic_h) : hr;
+        h_ = hr - r_ * ph_.a.H;
     };
-    gemv_prologue(sm.phase[0]);
+    auto phase_prologue = [&](const MegaPhase& nx) {
+        areg_valid = false;
+        if (nx.kind == 0) {
+            cta_rows(nx.g.N, cta, nx.rpc, pre_r0, pre_r1);
+            pre_bias = 0.f;
+            const int n = pre_r0 + warp + (lane / MEGA_NB) * MEGA_WARPS;
+            if (n < pre_r1 && nx.g.bias) pre_bias = __ldg(nx.g.bias + n);
+        } else if (nx.kind == 1 && nx.a.fixed_len > 0 && nx.a.key_valid == nullptr) {
+            if (cta < nx.a.rows * nx.a.H * nx.a.n_splits) {
+                int s_, h_, r_;
+                unit_of(nx, cta, s_, h_, r_);
+                decode_attention_load<MEGA_WARPS>(nx.a, s_, h_, r_, nx.a.row_slot ? sm.ctrl[4 + r_] : r_, nx.a.fixed_len, 0, tid, areg);
+            }
+            areg_valid = true;
+        }
+    };
+    phase_prologue(sm.phase[0]);
 
     for (int step = 0; step < mp.max_steps; ++step) {
         // uniform across the grid: all three were written before the previous grid barrier
@@ -246,11 +265,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                 const int L = a.fixed_len > 0 ? a.fixed_len : cur_pos + 1;
                 const int units = a.rows * a.H * a.n_splits;
                 for (int u = cta; u < units; u += G) {
-                    // exact for u < 2^16 (units <= rows * H * n_splits, a few thousand at most)
-                    const int hr = ph.magic_ns ? (int)__umulhi((unsigned)u, ph.magic_ns) : u, s = u - hr * a.n_splits;      // magic 0: divisor 1
-                    const int r = ph.magic_h ? (int)__umulhi((unsigned)hr, ph.magic_h) : hr, h = hr - r * a.H;
-                    decode_attention_body<MEGA_WARPS>(a, s, h, r, a.row_slot ? sm.ctrl[4 + r] : r, L, P, sm.u.attn.sc, sm.u.attn.red,
-                                                      sm.u.attn.stat, tid, tracing ? &mp.trace[(long long)pi * MEGA_TRACE_SLOTS + 6] : nullptr);
+                    int s, h, r;
+                    unit_of(ph, u, s, h, r);
+                    const int slot = a.row_slot ? sm.ctrl[4 + r] : r;
+                    if (!(areg_valid && u == cta)) decode_attention_load<MEGA_WARPS>(a, s, h, r, slot, L, P, tid, areg);
+                    decode_attention_body<MEGA_WARPS>(a, s, h, r, slot, L, P, sm.u.attn.sc, sm.u.attn.red, sm.u.attn.stat, tid, areg,
+                                                      tracing ? &mp.trace[(long long)pi * MEGA_TRACE_SLOTS + 6] : nullptr);
                     __syncthreads();
                 }
             } else {
@@ -262,7 +282,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
             MEGA_TRACE(4);
             sync_target += G;
             grid_arrive(mp.sync_counter);
-            gemv_prologue(sm.phase[cur ^ 1]);
+            phase_prologue(sm.phase[cur ^ 1]);
             grid_wait(mp.sync_counter, sync_target, mp.error_flag);
             MEGA_TRACE(5);
             cur ^= 1;
