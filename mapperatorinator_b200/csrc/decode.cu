@@ -9,6 +9,7 @@
 //
 // The GEMVs are weight-streaming (HBM-bound): one warp per output row, float4 coalesced reads of the [N, K] row-major
 // weight, activations for up to 8 batch rows staged in shared memory, fp32 accumulation in a fixed order.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "decode_device.cuh"
@@ -47,6 +48,20 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(DecAttnParams p) 
     AttnRegs<4> regs;
     decode_attention_load<4>(p, blockIdx.x, blockIdx.y, r, slot, L, P, threadIdx.x, regs);
     decode_attention_body<4>(p, blockIdx.x, blockIdx.y, r, slot, L, P, sc, red, stat, threadIdx.x, regs);
+}
+
+// batch form: one warp per (split, head, row) unit, 8 units per CTA (see decode_attention_warp_body)
+__global__ void __launch_bounds__(256) decode_attention_warp_kernel(DecAttnParams p) {
+    __shared__ float sc[8][128];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = blockIdx.x * 8 + warp;
+    if (u >= p.rows * p.H * p.n_splits) return;
+    const int L = p.fixed_len > 0 ? p.fixed_len : p.st->cur_len;
+    const int P = p.st ? p.st->prompt_len : 0;
+    const int hr = u / p.n_splits, s = u - hr * p.n_splits, r = hr / p.H, h = hr - r * p.H;
+    decode_attention_warp_body(p, s, h, r, p.row_slot ? p.row_slot[r] : r, L, P, sc[warp], lane);
 }
 
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleParams p) {
@@ -137,6 +152,14 @@ int launch_decode_attention(const DecAttnParams& p, cudaStream_t stream, bool pd
     MB_REQUIRE(p.out && p.ticket, "decode attention needs the merged-output buffer and its tickets");
     if (p.rows <= 0) return 0;
     g_prof_class = 1;
+    // Default: one CTA per unit with everything prefetched (the megakernel's phase body).  MB200_ATTN_BATCH=1 selects the
+    // one-warp-per-unit form for rows > 2 — the same arithmetic value for value (parity-tested), but measured SLOWER on B200
+    // (B = 64: 3.04 vs 3.30 TB/s, B = 8: 0.66 vs 1.15 TB/s): kept as the starting point for a persistent multi-unit kernel.
+    static const int batch_form = [] { const char* e = getenv("MB200_ATTN_BATCH"); return e ? atoi(e) : 0; }();
+    if (p.rows > 2 && batch_form) {
+        const int units = p.rows * p.H * p.n_splits;
+        return launch_with_attrs(decode_attention_warp_kernel, dim3((units + 7) / 8), dim3(256), 0, stream, pdl, p);
+    }
     return launch_with_attrs(decode_attention_kernel, dim3(p.n_splits, p.H, p.rows), dim3(128), 0, stream, pdl, p);
 }
 

@@ -402,6 +402,145 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// The same unit computed by ONE warp (batch throughput form: no CTA barriers, no shared-memory reductions; many independent warps
+// per SM hide the memory latency instead of one CTA prefetching everything).  Arithmetic is the 4-warp body's, value for value:
+// a score = 8-lane FMA chain + xor-shuffles 1, 2, 4; (m, l, p) with per-lane key order lane, lane+32, ... and the full shuffle tree;
+// o = four accumulation chains over keys = c mod 4 in ascending order, merged as (c0 + c1) + (c2 + c3).  A row therefore decodes
+// to the same bits whether it runs alone through the megakernel or inside a batch through this kernel.
+// sc: 128 floats of shared memory private to the warp.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void decode_attention_warp_body(const DecAttnParams& p, int s, int h, int r, int slot, int L, int P, float* sc, int lane) {
+    const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk), nk = k_end - k_begin;
+    const long long out_idx = ((long long)r * p.H + h) * p.n_splits + s;
+    float* outp = p.out + (long long)r * p.out_ld + h * 64 + 2 * lane;
+    if (nk <= 0) {
+        if (p.n_splits == 1) { outp[0] = 0.f; outp[1] = 0.f; return; }
+        if (lane == 0) { p.part_ml[out_idx * 2] = -INFINITY; p.part_ml[out_idx * 2 + 1] = 0.f; }
+    } else {
+        const int tok = (int)p.tok_stride;
+        const float* kb = p.kc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
+        const float* vb = p.vc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
+        const unsigned char* kv = p.key_valid ? p.key_valid + (long long)r * p.key_valid_ld + k_begin : nullptr;
+        const int n_prompt = P - k_begin;
+        const int sub = lane & 7, kq = lane >> 3;
+        const float* qp = p.q + (long long)r * p.q_ld + h * 64 + sub * 8;
+        const float4 q0 = ldcg4(qp), q1 = ldcg4(qp + 4);
+        // scores, 16 keys per batch (4 instructions x 4 keys): loads of a batch are all in flight before its first use
+        for (int k0 = 0; k0 < nk; k0 += 16) {
+            float4 ka[4], kb4[4];
+            unsigned char valid[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int kk = k0 + it * 4 + kq;
+                valid[it] = 1;
+                if (kk < nk) {
+                    const float* kr = kb + kk * tok + sub * 8;
+                    ka[it] = ldcg4(kr); kb4[it] = ldcg4(kr + 4);
+                    if (kv && kk < n_prompt) valid[it] = kv[kk];
+                } else {
+                    ka[it] = make_float4(0, 0, 0, 0); kb4[it] = make_float4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int kk = k0 + it * 4 + kq;
+                const float4 a = ka[it], b = kb4[it];
+                float d = q0.x * a.x;
+                d = fmaf(q0.y, a.y, d); d = fmaf(q0.z, a.z, d); d = fmaf(q0.w, a.w, d);
+                d = fmaf(q1.x, b.x, d); d = fmaf(q1.y, b.y, d); d = fmaf(q1.z, b.z, d); d = fmaf(q1.w, b.w, d);
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                if (kk < nk && sub == 0) sc[kk] = valid[it] ? d : -INFINITY;
+            }
+        }
+        __syncwarp();
+        float pv[4];                                     // p of keys lane, lane+32, lane+64, lane+96
+        float m = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = lane + 32 * t;
+            pv[t] = i < nk ? sc[i] : -INFINITY;
+            m = fmaxf(m, pv[t]);
+        }
+        m = warp_max(m);
+        float l = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = lane + 32 * t;
+            pv[t] = (i < nk && pv[t] != -INFINITY) ? expf(pv[t] - m) : 0.f;
+            if (i < nk) l += pv[t];
+        }
+        l = warp_sum(l);
+        float2 o[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {                    // 32 keys per pass, 16 V rows in flight at a time
+            if (32 * t < nk) {                           // uniform
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float2 vv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int kk = 32 * t + 16 * half + i;
+                        vv[i] = kk < nk ? ldcg2(vb + kk * tok + lane * 2) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int kk = 32 * t + 16 * half + i;
+                        const float pk = __shfl_sync(0xffffffffu, pv[t], kk & 31);
+                        if (kk < nk) {
+                            o[i & 3].x = fmaf(pk, vv[i].x, o[i & 3].x);
+                            o[i & 3].y = fmaf(pk, vv[i].y, o[i & 3].y);
+                        }
+                    }
+                }
+            }
+        }
+        const float vx = (o[0].x + o[1].x) + (o[2].x + o[3].x), vy = (o[0].y + o[1].y) + (o[2].y + o[3].y);
+        if (p.n_splits == 1) {
+            const float den = fmaf(1.f, l, 0.f);
+            const bool okd = l > 0.f && den > 0.f;
+            outp[0] = okd ? fmaf(1.f, vx, 0.f) / den : 0.f;
+            outp[1] = okd ? fmaf(1.f, vy, 0.f) / den : 0.f;
+            return;
+        }
+        p.part_o[out_idx * 64 + 2 * lane] = vx;
+        p.part_o[out_idx * 64 + 2 * lane + 1] = vy;
+        if (lane == 0) { p.part_ml[out_idx * 2] = m; p.part_ml[out_idx * 2 + 1] = l; }
+    }
+    // ticket + merge by the last split to arrive (warp-scope version of decode_attention_merge: bar.warp.sync orders the lanes'
+    // partial stores before lane 0's release, and the others' loads after its acquire)
+    __syncwarp();
+    int* ticket = p.ticket + r * p.H + h;
+    int t = 0;
+    if (lane == 0) asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t != p.n_splits - 1) return;
+    const int S = p.n_splits;
+    const long long base = ((long long)r * p.H + h) * S;
+    const float* ml = p.part_ml + base * 2;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const float* po = p.part_o + base * 64 + 2 * lane + e;
+        float mmax = -INFINITY, num = 0.f, den = 0.f;
+#pragma unroll 1
+        for (int q = 0; q < S; ++q) mmax = fmaxf(mmax, __ldcg(ml + q * 2));
+#pragma unroll 1
+        for (int q = 0; q < S; ++q) {
+            const float2 mv = ldcg2(ml + q * 2);
+            const float ov = __ldcg(po + q * 64);
+            if (mv.y > 0.f) {
+                const float w = expf(mv.x - mmax);
+                num = fmaf(w, ov, num);
+                den = fmaf(w, mv.y, den);
+            }
+        }
+        outp[e] = den > 0.f ? num / den : 0.f;
+    }
+    if (lane == 0) *ticket = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // fused logits-processor chain + token selection
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int SAMPLE_THREADS = 512;
