@@ -59,8 +59,8 @@ def prompt_for(i: int, streams) -> list:
     return base if i == 0 else base + streams[i - 1][-32:]
 
 
-# one `ncu --set full` capture of decode_megakernel<1> (63 tokens): 25.750 GB read + 4.3 MB written (profiles/r1_megakernel_ncu.md)
-MEGA_DRAM_BYTES_PER_LAUNCH = 25_750_469_000 + 4_253_440
+# one `ncu --set full` capture of decode_megakernel<1> (63 tokens): 25.731 GB read + 4.2 MB written (profiles/r1_megakernel_ncu.md)
+MEGA_DRAM_BYTES_PER_LAUNCH = 25_730_578_000 + 4_189_184
 
 
 def gen_kwargs(i: int, n_windows: int, P: int) -> dict:
