@@ -578,8 +578,9 @@ struct SampleSmem {
 };
 
 // The whole logits-processor chain + token selection + append for batch row b (one CTA of SAMPLE_THREADS threads).
-// Deliberately NOT inlined and with rolled vocabulary loops: it runs once per token on one CTA, and inside the persistent
-// megakernel its code must not push the per-layer phases out of the 32 KB L1.5 instruction cache.
+// Deliberately NOT inlined and with rolled vocabulary loops: it runs once per token on one CTA; inlined and unrolled it was 70 KB of
+// the megakernel's 130 KB of code.  (A cold/warm re-run experiment later showed the per-layer phases are NOT instruction-fetch bound,
+// so this is about code size and register pressure of the caller, not about the 32 KB L1.5 instruction cache.)
 // Returns after the "last CTA" bookkeeping; the caller decides how the grid synchronises afterwards.
 static __device__ __noinline__ void sample_body(const SampleParams& p, int b, SampleSmem& sm) {
     float* s = sm.s;

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                     if (n < r1 && b < ph.g.B && ph.g.R) r_pref = __ldcg(ph.g.R + (long long)b * ph.g.r_ld + n);
                 }
                 // trace mode runs the staging twice through the SAME code: pass 0 (slots 8, 9, 10) is what production pays, pass 1
-                // (slots 6, 7, 1) repeats it with instruction cache / TLB / L2 state warm — the difference is fetch, not data, latency
+                // (slots 6, 7, 1) repeats it with instruction cache / TLB / L2 state warm — measured: no difference, i.e. the phases are not fetch-bound
                 for (int rep = tracing ? 0 : 1; rep < 2; ++rep) {
                     MEGA_TRACE(rep ? 6 : 8);
                     gemv_stage_x<MEGA_NB, MEGA_THREADS>(ph.g, 0, sm.u.xs, sm.ln_red, tid,
