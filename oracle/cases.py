@@ -53,6 +53,21 @@ def generate_cases():
     }
 
 
+def long_context_cases():
+    """name -> (prompt, generate_kwargs, pcm_seed): prompts beyond 128 tokens (self-attention cache in several 64-key splits:
+    3 splits at 174 tokens, 10 splits at 612), batch of 2 with left padding on row 0."""
+    out = {}
+    for P, new in ((150, 24), (600, 12)):
+        g = torch.Generator().manual_seed(P)
+        prompt = torch.randint(17, 3600, (2, P), generator=g)
+        prompt[:, :4] = torch.tensor([3700, 3705, 1, 9])
+        prompt[0, :7] = 0                                          # left padding on row 0
+        prompt[0, 7:11] = torch.tensor([3700, 3705, 1, 9])
+        gk = dict(GK, max_length=P + new, min_new_tokens=new, lookback_time=0.0, lookahead_time=0.0, context_type="map")
+        out[f"long_P{P}"] = (prompt, gk, 11)
+    return out
+
+
 def teacher_forcing_case(cfg):
     g = torch.Generator().manual_seed(3)
     ids = torch.randint(17, cfg.vocab_size_in, (2, 21), generator=g)

@@ -62,6 +62,11 @@ def main():
             ids, stats = model_generate(model, tok2, dict(mk), dict(gk))
             gen_out[f"{flavour}/{cname}/ids"] = ids.numpy()
             gen_out[f"{flavour}/{cname}/counts"] = np.array(stats["generated_tokens_per_sample"])
+        if flavour == "torchaudio":                               # long prompts: decoder-side only, one flavour is enough
+            for cname, (prompt, gk, seed) in cases.long_context_cases().items():
+                mk = dict(inputs=cases.model_pcm(cfg, prompt.shape[0], seed), decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0))
+                ids, _ = model_generate(model, tok2, dict(mk), dict(gk))
+                gen_out[f"{flavour}/{cname}/ids"] = ids.numpy()
         ids, mask = cases.teacher_forcing_case(cfg)
         out = model(frames=cases.model_pcm(cfg, 2, 1), decoder_input_ids=ids, decoder_attention_mask=mask)
         gen_out[f"{flavour}/teacher_logits"] = out.logits.float().numpy()[:, ::3, ::37]

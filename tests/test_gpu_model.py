@@ -83,23 +83,18 @@ def test_greedy_generate_bit_exact(tiny, layout, gen_gold, case, path):
 
 
 @pytest.mark.parametrize("path", ["megakernel", "graph"])
-@pytest.mark.parametrize("P,new", [(150, 24), (600, 12)])
-def test_greedy_generate_long_context(tiny, layout, P, new, path):
+@pytest.mark.parametrize("case", list(cases.long_context_cases()))
+def test_greedy_generate_long_context(tiny, layout, gen_gold, case, path):
     """Contexts beyond 128 tokens switch the self-attention cache to 64-key splits merged by the last-arriving split (3 splits at
-    174 tokens; 10 splits at 612 tokens = the rolled many-split merge).  The golden cases all stay below 64 tokens, so this
-    case is checked against the oracle only (the oracle itself is pinned to the reference on the short cases)."""
+    174 tokens; 10 splits at 612 tokens = the rolled many-split merge).  Checked against the oracle AND the reference fixture
+    (tests/golden, unmodified `server.model_generate`)."""
     from mapperatorinator_b200.server import model_generate
     from oracle import generate as go
     flavour, cfg, sd, model = tiny
     if flavour != "torchaudio":
         pytest.skip("one mel flavour is enough for the decoder-side path")
-    g = torch.Generator().manual_seed(P)
-    prompt = torch.randint(17, 3600, (2, P), generator=g)
-    prompt[:, :4] = torch.tensor([3700, 3705, 1, 9])
-    prompt[0, :7] = 0                                          # left padding on row 0
-    prompt[0, 7:11] = torch.tensor([3700, 3705, 1, 9])
-    gk = dict(cases.GK, max_length=P + new, min_new_tokens=new, lookback_time=0.0, lookahead_time=0.0, context_type="map")
-    mk = dict(inputs=cases.model_pcm(cfg, 2, 11), decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0))
+    prompt, gk, seed = cases.long_context_cases()[case]
+    mk = dict(inputs=cases.model_pcm(cfg, 2, seed), decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0))
     want, _ = go.model_generate(sd, cfg, layout, dict(mk), dict(gk))
     model.engine.set_option("mega", 1 if path == "megakernel" else 0)
     try:
@@ -110,6 +105,7 @@ def test_greedy_generate_long_context(tiny, layout, P, new, path):
     if not torch.equal(got, want):
         r, c = (got != want).nonzero()[0].tolist()
         pytest.fail(f"first divergence vs oracle at row {r} col {c}: got {got[r, c].item()} want {want[r, c].item()}")
+    assert np.array_equal(got.numpy(), gen_gold[f"{flavour}/{case}/ids"]), "differs from the reference fixture"
 
 
 def test_sampling_is_valid_and_seeded(tiny, layout):

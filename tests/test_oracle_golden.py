@@ -54,6 +54,17 @@ def test_greedy_ids_bit_exact(gen_gold, layout, flavour, case):
     assert stats["generated_tokens_per_sample"] == gen_gold[f"{flavour}/{case}/counts"].tolist()
 
 
+@pytest.mark.parametrize("case", list(cases.long_context_cases()))
+def test_greedy_ids_long_context(gen_gold, layout, case):
+    """Prompts of 150 and 600 tokens (left-padded batch of 2): the oracle against the unmodified reference's model_generate."""
+    cfg = tiny_model_config(mel=cases.MODEL_FLAVOURS["torchaudio"])
+    sd = init_model_state_dict(cfg, 0)
+    prompt, gk, seed = cases.long_context_cases()[case]
+    mk = dict(inputs=cases.model_pcm(cfg, prompt.shape[0], seed), decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0))
+    ids, _ = gen_oracle.model_generate(sd, cfg, layout, mk, dict(gk))
+    assert np.array_equal(ids.numpy(), gen_gold[f"torchaudio/{case}/ids"])
+
+
 @pytest.mark.parametrize("case", list(cases.processor_cases()))
 def test_processor_chain(layout, case):
     gold = np.load(os.path.join(GOLDEN, "processors_reference.npz"))
