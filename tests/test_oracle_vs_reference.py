@@ -41,3 +41,26 @@ def test_v29_dims_single_step_logits():
         out = wo.forward_logits(sd, cfg, pcm, ids, ids.ne(0))
     assert torch.allclose(out, ref, rtol=1e-3, atol=1e-3), (out - ref).abs().max()
     assert torch.equal(out.argmax(-1), ref.argmax(-1))
+
+
+def test_diffusion_host_helpers_match_reference():
+    """`timestep_embedding`, the seq_c layout of `events_to_sequence` (diffusion_pipeline.py:380-387) and the band mask loop
+    (:146-148) — the host-side tensor preparation around stage (iii) — against the reference's own functions."""
+    from mapperatorinator_b200 import diffusion as md
+    ref_import.install_stubs()
+    from osu_diffusion import timestep_embedding as ref_te
+    g = torch.Generator().manual_seed(4)
+    T = 37
+    seq_o = torch.rand(T, generator=g) * 180000.0
+    seq_d = torch.rand(T, generator=g) * 400.0
+    types = torch.randint(0, 16, (T,), generator=g)
+    for v in (seq_o * 0.1, seq_d):
+        assert torch.equal(md.timestep_embedding(v, 128), ref_te(v, 128))
+    want = torch.cat([ref_te(seq_o * 0.1, 128).T, ref_te(seq_d, 128).T, torch.nn.functional.one_hot(types, 16).float().T], 0)
+    assert torch.equal(md.build_context(seq_o, seq_d, types), want)
+    # band mask: the reference fills it column by column (diffusion_pipeline.py:146-148)
+    L, w = 50, 8
+    ref_mask = torch.full((L, L), True, dtype=torch.bool)
+    for i in range(L):
+        ref_mask[max(0, i - w): min(L, i + w), i] = False
+    assert torch.equal(md.band_attention_mask(L, w), ref_mask)
