@@ -121,3 +121,36 @@ def test_product_refuses_without_gpu():
     from mapperatorinator_b200.engine import ModelEngine
     with pytest.raises(RuntimeError):
         ModelEngine(tiny_model_config(), {})
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints ONE JSON line with the contract's keys;
+    bounded sample: one window here."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-windows", "1",
+                          "--cpu-threads", "8"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "event tokens/sec end-to-end" and d["unit"] == "tokens/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f32"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 8 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["windows"] == 211 and "workload" in d["config"]
+
+
+def test_clock_sampler_parses_nvidia_smi_rows():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    cs = bench.ClockSampler(0)
+    cs.rows = ["1965, 1965, Not Active, Not Active, Not Active, Active\n", "1950, 1965, Not Active, Not Active, Not Active, Not Active\n",
+               "garbage\n", "1965, 1965, Not Active, Active, Not Active, Not Active\n"]
+    s = cs.summary()
+    assert s["sm_mhz"] == 1965.0 and s["sm_max_mhz"] == 1965.0 and s["samples"] == 3
+    assert s["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
