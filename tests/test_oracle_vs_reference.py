@@ -64,3 +64,35 @@ def test_diffusion_host_helpers_match_reference():
     for i in range(L):
         ref_mask[max(0, i - w): min(L, i + w), i] = False
     assert torch.equal(md.band_attention_mask(L, w), ref_mask)
+
+
+def test_v29_dims_bench_window_greedy_ids():
+    """The bench workload's second window (50-token prompt, look-back + look-ahead processors, min_new_tokens) at FULL whisper-small
+    dimensions through the unmodified reference `server.model_generate`, against the oracle: 10 greedy tokens, ids bit-exact.
+    (The bench then asserts GPU ids == oracle ids on its CPU sample, closing the chain reference -> oracle -> engine at v29 dims.)"""
+    import dataclasses
+    import os
+    import sys
+    from mapperatorinator_b200 import MelConfig, TokenLayout, v29_model_config
+    from mapperatorinator_b200.weights import init_model_state_dict
+    from oracle import generate as go, ref_build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    cfg = dataclasses.replace(v29_model_config(), mel=MelConfig("torchaudio", n_mels=80))
+    model, tok, _ = ref_build.reference_model(cfg, mel_impl="torchaudio")          # installs the import stubs
+    from osuT5.osuT5.inference.server import model_generate
+    sd = init_model_state_dict(cfg, 0)
+    ref_build.load_state_dict_into_reference(model, sd)
+    layout = TokenLayout.from_tokenizer(tok)
+    g = torch.Generator().manual_seed(0)
+    pcm = torch.randn(1, cfg.samples_per_window, generator=g) * 0.1
+    prompt = torch.tensor([bench.prompt_for(1, [list(range(100, 164))])])
+    P = prompt.shape[1]
+    gk = bench.gen_kwargs(1, 211, P)
+    gk.update(max_length=P + 10, min_new_tokens=10, precision="fp32")
+    mk = dict(inputs=pcm, decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0))
+    with torch.no_grad():
+        ref_ids, _ = model_generate(model, tok, dict(mk), dict(gk))
+        ora_ids, _ = go.model_generate(sd, cfg, layout, dict(mk), dict(gk))
+    assert torch.equal(ref_ids, ora_ids), (ref_ids[0, P:].tolist(), ora_ids[0, P:].tolist())
