@@ -167,6 +167,7 @@ extern "C" void mb200_model_destroy(mb200_model* m) {
     for (auto& g : m->prefill_graphs) cudaGraphExecDestroy(g.second.first);
     for (const float* w : m->tc_weights) tc_unregister_weight(w);
     for (auto& kv : m->mega_phases) delete kv.second.first;
+    for (auto& e : m->mega_ev) if (e) cudaEventDestroy(e);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     mel_plan_destroy(m->mel);
     if (m->h_flag) cudaFreeHost(m->h_flag);
