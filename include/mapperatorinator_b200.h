@@ -155,6 +155,8 @@ int mb200_dit_sample_loop(mb200_dit* d, const float* z, const float* c, const fl
 int64_t mb200_launch_count(void);
 /* option "pdl": 1 = capture the token-step graph with programmatic dependent launch edges. */
 int mb200_model_set_option(mb200_model* m, const char* name, int32_t value);
+/* option "graph": 1 (default) = every step of mb200_dit_sample_loop is one replay of a captured CUDA graph, 0 = eager launches. */
+int mb200_dit_set_option(mb200_dit* d, const char* name, int32_t value);
 /* Re-runs the token step eagerly `iters` times on the state of the last generate() call with CUDA events around every
  * decode-path launch: out_us[0..2] = device us per token in {gemv, split-KV attention, logits+sample} kernels,
  * out_us[3] = launches per token packed as gemv*1e6 + attention*1e3 + sample. */

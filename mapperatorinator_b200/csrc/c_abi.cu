@@ -53,7 +53,7 @@ extern "C" int mb200_op_gemm(const float* A, int64_t lda, const float* W, int64_
     g.gate = gate; g.gate_ld = gate_ld; g.gate_rpb = gate_rpb > 0 ? gate_rpb : 1;
     g.R = residual ? plain_map(residual, ldr) : RowMap{nullptr, 0, 0, 0};
     g.M = M; g.N = N; g.K = K;
-    return launch_gemm(g, (cudaStream_t)stream);
+    return launch_gemm(g, (cudaStream_t)stream, default_gemm_ctx());
 }
 
 extern "C" int mb200_op_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, const float* bias, int32_t act,
@@ -63,15 +63,19 @@ extern "C" int mb200_op_gemm_tc(const float* A, int64_t lda, const float* W, int
     g.gate = nullptr; g.gate_ld = 0; g.gate_rpb = 1;
     g.R = residual ? plain_map(residual, ldr) : RowMap{nullptr, 0, 0, 0};
     g.M = M; g.N = N; g.K = K;
-    int s = tc_register_weight(W, (long long)N * ldw);
+    GemmCtx* ctx = default_gemm_ctx();
+    int s = ctx->register_weight(W, (long long)N * ldw);
     if (s) return s;
-    MB_REQUIRE(tc_gemm_eligible(g), "problem not eligible for the tcgen05 path (M >= 512, K % 4 == 0, 16-byte aligned operands)");
-    s = launch_gemm_tc(g, (cudaStream_t)stream);
+    if (!tc_gemm_eligible(g, ctx)) {
+        ctx->unregister_weight(W);
+        MB_REQUIRE(false, "problem not eligible for the tcgen05 path (M >= 512, K % 4 == 0, 16-byte aligned operands)");
+    }
+    s = launch_gemm_tc(g, (cudaStream_t)stream, ctx);
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-    tc_unregister_weight(W);      // W belongs to the caller (a torch tensor whose address may be recycled)
+    ctx->unregister_weight(W);      // W belongs to the caller (a torch tensor whose address may be recycled)
     if (s) return s;
     MB_CUDA_CHECK(e);
-    MB_REQUIRE(tc_gemm_error() == 0, "tcgen05 GEMM pipeline wait timed out");
+    MB_REQUIRE(ctx->error() == 0, "tcgen05 GEMM pipeline wait timed out");
     return 0;
 }
 

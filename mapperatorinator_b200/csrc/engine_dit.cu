@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -92,14 +94,35 @@ __global__ void dit_cfg_out_kernel(const float* __restrict__ o4, int N, int T, f
     }
 }
 
-struct StepConst { float sqrt_recip, sqrt_recipm1, min_log, max_log, coef1, coef2, nonzero; };
+struct StepConst { float t, sqrt_recip, sqrt_recipm1, min_log, max_log, coef1, coef2, nonzero; };   // one row of the host schedule table
 
-// one p_sample update (gaussian_diffusion.py:312-358, 454-466) for every (n, ch, t)
-__global__ void dit_update_kernel(const float* __restrict__ o4, const float* __restrict__ x, const float* __restrict__ z,
+// Step-varying inputs are addressed through a device-resident step counter so that ONE captured CUDA graph serves every step:
+// this kernel copies step k's adaLN modulation rows into the fixed buffers the graph's GEMM / LayerNorm nodes point at.
+//   mods_all [depth][steps*N][6d] -> mods_cur [depth][N][6d];   fmod_all [steps*N][2d] -> fmod_cur [N][2d]
+__global__ void dit_gather_mods_kernel(const float4* __restrict__ mods_all, const float4* __restrict__ fmod_all, const int* __restrict__ step_ptr,
+                                       int depth, int steps, int N, int d4 /* d / 4 */, float4* __restrict__ mods_cur, float4* __restrict__ fmod_cur) {
+    const int k = *step_ptr;
+    const long long per_layer = (long long)N * 6 * d4, total_m = (long long)depth * per_layer, total = total_m + (long long)N * 2 * d4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        if (i < total_m) {
+            const long long l = i / per_layer, r = i - l * per_layer;
+            mods_cur[i] = mods_all[(l * steps + k) * per_layer + r];
+        } else {
+            const long long r = i - total_m;
+            fmod_cur[r] = fmod_all[(long long)k * N * 2 * d4 + r];
+        }
+    }
+}
+
+// one p_sample update (gaussian_diffusion.py:312-358, 454-466) for every (n, ch, t), in place (each element depends on its own
+// index only); the step's constants and noise slice are read through the device step counter
+__global__ void dit_update_kernel(const float* __restrict__ o4, float* __restrict__ x, const float* __restrict__ z,
                                   const unsigned char* __restrict__ inpaint, const float* __restrict__ noise, int N, int T, float cfg_scale,
-                                  StepConst sc, float* __restrict__ x_new) {
+                                  const StepConst* __restrict__ sched, const int* __restrict__ step_ptr) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * 2 * T) return;
+    const int k = *step_ptr;
+    const StepConst sc = sched[k];
     const int n = idx / (2 * T), rem = idx - n * 2 * T, ch = rem / T, t = rem - ch * T, half_n = N / 2;
     const float cond = o4[((long long)(n % half_n) * T + t) * 4 + ch];
     const float unc = o4[((long long)(half_n + n % half_n) * T + t) * 4 + ch];
@@ -112,8 +135,12 @@ __global__ void dit_update_kernel(const float* __restrict__ o4, const float* __r
     if (inpaint && !inpaint[idx]) x0 = z[idx];
     x0 = fminf(fmaxf(x0, -2.0f), 2.0f);
     const float mean = sc.coef1 * x0 + sc.coef2 * xt;
-    x_new[idx] = mean + sc.nonzero * expf(0.5f * logvar) * noise[idx];
+    x[idx] = mean + sc.nonzero * expf(0.5f * logvar) * noise[(long long)k * N * 2 * T + idx];
 }
+
+__global__ void dit_step_advance_kernel(int* step_ptr) { *step_ptr += 1; }
+
+struct BlockW { const float *in_w, *in_b, *out_w, *out_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *ada_w, *ada_b; };
 
 }  // namespace
 
@@ -122,11 +149,20 @@ struct mb200_dit {
     std::unordered_map<std::string, std::vector<float>> host_w;
     bool finalized = false;
     DevBufD arena;
-    std::unordered_map<std::string, const float*> w;   // device pointers by reference name
+    // device pointers, resolved ONCE at finalize (no name lookups on the step path)
+    const float *ctx_w = nullptr, *ctx_b = nullptr, *t0_w = nullptr, *t0_b = nullptr, *t2_w = nullptr, *t2_b = nullptr, *y0_w = nullptr,
+                *y0_b = nullptr, *y2_w = nullptr, *y2_b = nullptr, *fada_w = nullptr, *fada_b = nullptr, *flin_w = nullptr, *flin_b = nullptr;
+    std::vector<BlockW> blocks;
     const float *pos_freqs = nullptr, *t_freqs = nullptr;
-    DevBufD a0, x, h, qkv, att, ffn, o4, temb, te1, te, ye1, ye, bcond, mods, fmod, tvals, state0, state1;
-    int mod_steps = 0;
-    std::vector<const float*> tc_weights;
+    DevBufD a0, x, h, qkv, att, ffn, o4, temb, te1, te, ye1, ye, bcond, mods, fmod, tvals;
+    // sampling loop: engine-owned copies of the call's inputs + the step-indexed tables, so the captured step graph never sees a
+    // caller pointer
+    DevBufD state, z_in, c_in, y_in, noise_in, inpaint_in, dense_in, sched, step_ctr, mods_cur, fmod_cur;
+    std::map<std::tuple<int, int, int, int, int>, std::pair<cudaGraphExec_t, long long>> step_graphs;   // (N, T, mask mode, band, in-paint) -> graph, nodes
+    cudaStream_t cap_stream = nullptr;
+    bool use_graph = true;
+    float graph_cfg_scale = 0.f; const void* graph_noise = nullptr; const void* graph_mods = nullptr;   // what the cached graphs baked
+    GemmCtx gemm;
 };
 
 extern "C" int mb200_dit_create(mb200_dit** out, const mb200_dit_config* cfg) {
@@ -143,7 +179,9 @@ extern "C" int mb200_dit_create(mb200_dit** out, const mb200_dit_config* cfg) {
 
 extern "C" void mb200_dit_destroy(mb200_dit* d) {
     if (!d) return;
-    for (const float* w : d->tc_weights) tc_unregister_weight(w);
+    for (auto& g : d->step_graphs) cudaGraphExecDestroy(g.second.first);
+    if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
+    d->gemm.destroy();
     delete d;
 }
 
@@ -197,17 +235,37 @@ extern "C" int mb200_dit_finalize(mb200_dit* dd) {
     }
     MB_TRY(dd->arena.ensure(pack.size() * 4));
     MB_CUDA_CHECK(cudaMemcpy(dd->arena.p, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice));
-    for (auto& kv : offs) dd->w[kv.first] = dd->arena.f() + kv.second;
-    // tf32 "lo" mirrors for the tensor-core GEMMs (every 2-D weight of the blocks and the embedders)
+    auto W = [&](const std::string& n) -> const float* { return dd->arena.f() + offs.at(n); };
+    dd->ctx_w = W("context_embedder.mlp.0.weight"); dd->ctx_b = W("context_embedder.mlp.0.bias");
+    dd->t0_w = W("t_embedder.mlp.0.weight"); dd->t0_b = W("t_embedder.mlp.0.bias"); dd->t2_w = W("t_embedder.mlp.2.weight"); dd->t2_b = W("t_embedder.mlp.2.bias");
+    dd->y0_w = W("y_embedder.class_embedding.0.weight"); dd->y0_b = W("y_embedder.class_embedding.0.bias");
+    dd->y2_w = W("y_embedder.class_embedding.2.weight"); dd->y2_b = W("y_embedder.class_embedding.2.bias");
+    dd->fada_w = W("final_layer.adaLN_modulation.1.weight"); dd->fada_b = W("final_layer.adaLN_modulation.1.bias");
+    dd->flin_w = W("final_layer.linear.weight"); dd->flin_b = W("final_layer.linear.bias");
+    for (int i = 0; i < c.depth; ++i) {
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        dd->blocks.push_back(BlockW{W(p + "attn.in_proj_weight"), W(p + "attn.in_proj_bias"), W(p + "attn.out_proj.weight"), W(p + "attn.out_proj.bias"),
+                                    W(p + "mlp.fc1.weight"), W(p + "mlp.fc1.bias"), W(p + "mlp.fc2.weight"), W(p + "mlp.fc2.bias"),
+                                    W(p + "adaLN_modulation.1.weight"), W(p + "adaLN_modulation.1.bias")});
+    }
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&dd->gemm.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // tf32 hi / lo mirrors for the tensor-core GEMMs (every 2-D weight of the blocks and the embedders)
     for (const auto& n : names)
-        if (n.find("weight") != std::string::npos && sizes.at(n) >= (size_t)64 * 32) {
-            dd->tc_weights.push_back(dd->w[n]);
-            MB_TRY(tc_register_weight(dd->w[n], (long long)sizes.at(n)));
-        }
+        if (n.find("weight") != std::string::npos && sizes.at(n) >= (size_t)64 * 32) MB_TRY(dd->gemm.register_weight(W(n), (long long)sizes.at(n)));
     MB_CUDA_CHECK(cudaDeviceSynchronize());
-    dd->pos_freqs = dd->w["__pos_freqs"]; dd->t_freqs = dd->w["__t_freqs"];
+    dd->pos_freqs = W("__pos_freqs"); dd->t_freqs = W("__t_freqs");
     MB_REQUIRE(dd->host_w.at("context_embedder.mlp.0.weight").size() == (size_t)d * (c.in_channels * c.pos_freq_dim + c.context_size),
                "context_embedder shape mismatch");
+    {   // all scratch for the largest call, allocated once: the captured step graphs hold these pointers
+        const size_t R = (size_t)std::max(2, c.max_batch) * c.max_seq_len;
+        const size_t K0 = (size_t)c.in_channels * c.pos_freq_dim + c.context_size;
+        MB_TRY(dd->gemm.reserve((size_t)64 << 20, R * std::max((size_t)d * c.mlp_ratio, K0) * 8 + 1024));
+        dd->gemm.frozen = true;
+    }
     dd->host_w.clear();
     dd->finalized = true;
     return 0;
@@ -233,6 +291,7 @@ int ln_mod(const float* x, float* y, const float* shift, const float* scale, lon
 int prepare_conditioning(mb200_dit* dd, const float* tvals_host, int steps, int N, const float* y, cudaStream_t st) {
     const auto& c = dd->cfg;
     const int d = c.hidden, RS = steps * N;
+    GemmCtx* gc = &dd->gemm;
     MB_TRY(dd->tvals.ensure((size_t)RS * 4)); MB_TRY(dd->temb.ensure((size_t)RS * c.t_freq_dim * 4));
     MB_TRY(dd->te1.ensure((size_t)RS * d * 4)); MB_TRY(dd->te.ensure((size_t)RS * d * 4));
     MB_TRY(dd->ye1.ensure((size_t)N * d * 4)); MB_TRY(dd->ye.ensure((size_t)N * d * 4));
@@ -242,56 +301,53 @@ int prepare_conditioning(mb200_dit* dd, const float* tvals_host, int steps, int 
     MB_CUDA_CHECK(cudaStreamSynchronize(st));
     dit_temb_kernel<<<RS, 128, 0, st>>>(dd->tvals.f(), dd->t_freqs, c.t_freq_dim, dd->temb.f());
     MB_LAUNCH_CHECK();
-    auto& w = dd->w;
     {
-        GemmParams g = gb(dd->temb.f(), c.t_freq_dim, w["t_embedder.mlp.0.weight"], c.t_freq_dim, dd->te1.f(), d, w["t_embedder.mlp.0.bias"], RS, d, c.t_freq_dim);
+        GemmParams g = gb(dd->temb.f(), c.t_freq_dim, dd->t0_w, c.t_freq_dim, dd->te1.f(), d, dd->t0_b, RS, d, c.t_freq_dim);
         g.act = ACT_SILU;
-        MB_TRY(launch_gemm(g, st));
-        MB_TRY(launch_gemm(gb(dd->te1.f(), d, w["t_embedder.mlp.2.weight"], d, dd->te.f(), d, w["t_embedder.mlp.2.bias"], RS, d, d), st));
-        GemmParams gy = gb(y, c.class_size, w["y_embedder.class_embedding.0.weight"], c.class_size, dd->ye1.f(), d,
-                           w["y_embedder.class_embedding.0.bias"], N, d, c.class_size);
+        MB_TRY(launch_gemm(g, st, gc));
+        MB_TRY(launch_gemm(gb(dd->te1.f(), d, dd->t2_w, d, dd->te.f(), d, dd->t2_b, RS, d, d), st, gc));
+        GemmParams gy = gb(y, c.class_size, dd->y0_w, c.class_size, dd->ye1.f(), d, dd->y0_b, N, d, c.class_size);
         gy.act = ACT_SILU;
-        MB_TRY(launch_gemm(gy, st));
-        MB_TRY(launch_gemm(gb(dd->ye1.f(), d, w["y_embedder.class_embedding.2.weight"], d, dd->ye.f(), d, w["y_embedder.class_embedding.2.bias"], N, d, d), st));
+        MB_TRY(launch_gemm(gy, st, gc));
+        MB_TRY(launch_gemm(gb(dd->ye1.f(), d, dd->y2_w, d, dd->ye.f(), d, dd->y2_b, N, d, d), st, gc));
     }
     dit_cond_kernel<<<RS, 128, 0, st>>>(dd->te.f(), dd->ye.f(), N, d, dd->bcond.f());
     MB_LAUNCH_CHECK();
-    for (int l = 0; l < c.depth; ++l) {
-        std::string p = "blocks." + std::to_string(l) + ".adaLN_modulation.1.";
-        MB_TRY(launch_gemm(gb(dd->bcond.f(), d, w[p + "weight"], d, dd->mods.f() + (size_t)l * RS * 6 * d, 6 * d, w[p + "bias"], RS, 6 * d, d), st));
-    }
-    MB_TRY(launch_gemm(gb(dd->bcond.f(), d, w["final_layer.adaLN_modulation.1.weight"], d, dd->fmod.f(), 2 * d,
-                          w["final_layer.adaLN_modulation.1.bias"], RS, 2 * d, d), st));
-    dd->mod_steps = steps;
+    for (int l = 0; l < c.depth; ++l)
+        MB_TRY(launch_gemm(gb(dd->bcond.f(), d, dd->blocks[l].ada_w, d, dd->mods.f() + (size_t)l * RS * 6 * d, 6 * d, dd->blocks[l].ada_b, RS, 6 * d, d), st, gc));
+    MB_TRY(launch_gemm(gb(dd->bcond.f(), d, dd->fada_w, d, dd->fmod.f(), 2 * d, dd->fada_b, RS, 2 * d, d), st, gc));
     return 0;
 }
 
-int ensure_work(mb200_dit* dd, int N, int T) {
+// activations for the largest (N, T) the engine was created for: allocated on first use, never moved afterwards
+int ensure_work(mb200_dit* dd) {
     const auto& c = dd->cfg;
     const int d = c.hidden;
-    const size_t R = (size_t)N * T;
+    const size_t R = (size_t)std::max(2, c.max_batch) * c.max_seq_len;
     const int K0 = c.in_channels * c.pos_freq_dim + c.context_size;
     MB_TRY(dd->a0.ensure(R * K0 * 4)); MB_TRY(dd->x.ensure(R * d * 4)); MB_TRY(dd->h.ensure(R * d * 4));
     MB_TRY(dd->qkv.ensure(R * 3 * d * 4)); MB_TRY(dd->att.ensure(R * d * 4)); MB_TRY(dd->ffn.ensure(R * d * c.mlp_ratio * 4));
     MB_TRY(dd->o4.ensure(R * 4 * 4));
+    MB_TRY(dd->mods_cur.ensure((size_t)c.depth * c.max_batch * 6 * d * 4)); MB_TRY(dd->fmod_cur.ensure((size_t)c.max_batch * 2 * d * 4));
     return 0;
 }
 
-// one DiT forward at conditioning row block `step` -> o4[(n,t), 4]
-int dit_forward(mb200_dit* dd, const float* xstate, const float* cctx, int N, int T, int step, int steps_total, const mb200_dit_mask* mask,
-                cudaStream_t st) {
+// one DiT forward with the modulation rows at mods [depth][N][6d] / fm [N][2d] -> o4[(n,t), 4]
+int dit_forward(mb200_dit* dd, const float* xstate, const float* cctx, int N, int T, const float* mods, const float* fm,
+                const mb200_dit_mask* mask, cudaStream_t st) {
     const auto& c = dd->cfg;
-    const int d = c.hidden, f = d * c.mlp_ratio, R = N * T, RS = steps_total * N;
+    const int d = c.hidden, f = d * c.mlp_ratio, R = N * T;
     const int K0 = c.in_channels * c.pos_freq_dim + c.context_size;
-    auto& w = dd->w;
+    GemmCtx* gc = &dd->gemm;
     dit_embed_kernel<<<dim3(T, N), 128, 0, st>>>(xstate, cctx, dd->pos_freqs, N, T, c.in_channels, c.context_size, c.pos_freq_dim, dd->a0.f());
     MB_LAUNCH_CHECK();
-    MB_TRY(launch_gemm(gb(dd->a0.f(), K0, w["context_embedder.mlp.0.weight"], K0, dd->x.f(), d, w["context_embedder.mlp.0.bias"], R, d, K0), st));
+    ++g_launch_count;
+    MB_TRY(launch_gemm(gb(dd->a0.f(), K0, dd->ctx_w, K0, dd->x.f(), d, dd->ctx_b, R, d, K0), st, gc));
     for (int l = 0; l < c.depth; ++l) {
-        std::string p = "blocks." + std::to_string(l) + ".";
-        const float* mod = dd->mods.f() + ((size_t)l * RS + (size_t)step * N) * 6 * d;   // rows n = 0..N-1 of this step
+        const BlockW& w = dd->blocks[l];
+        const float* mod = mods + (size_t)l * N * 6 * d;   // rows n = 0..N-1
         MB_TRY(ln_mod(dd->x.f(), dd->h.f(), mod + 0, mod + d, 6 * d, T, R, d, st));
-        MB_TRY(launch_gemm(gb(dd->h.f(), d, w[p + "attn.in_proj_weight"], d, dd->qkv.f(), 3 * d, w[p + "attn.in_proj_bias"], R, 3 * d, d), st));
+        MB_TRY(launch_gemm(gb(dd->h.f(), d, w.in_w, d, dd->qkv.f(), 3 * d, w.in_b, R, 3 * d, d), st, gc));
         AttentionParams a{};
         a.q = dd->qkv.f(); a.q_ld = 3 * d; a.q_bs = (long long)T * 3 * d;
         a.k = dd->qkv.f() + d; a.k_ld = 3 * d; a.k_bs = a.q_bs;
@@ -301,25 +357,24 @@ int dit_forward(mb200_dit* dd, const float* xstate, const float* cctx, int N, in
         a.mask_mode = mask ? mask->mask_mode : MASK_NONE; a.band = mask ? mask->band : 0; a.dense = mask ? mask->dense_mask : nullptr;
         MB_TRY(launch_attention(a, st));
         {
-            GemmParams g = gb(dd->att.f(), d, w[p + "attn.out_proj.weight"], d, dd->x.f(), d, w[p + "attn.out_proj.bias"], R, d, d);
+            GemmParams g = gb(dd->att.f(), d, w.out_w, d, dd->x.f(), d, w.out_b, R, d, d);
             g.gate = mod + 2 * d; g.gate_ld = 6 * d; g.gate_rpb = T; g.R = plain_map(dd->x.f(), d);
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, gc));
         }
         MB_TRY(ln_mod(dd->x.f(), dd->h.f(), mod + 3 * d, mod + 4 * d, 6 * d, T, R, d, st));
         {
-            GemmParams g = gb(dd->h.f(), d, w[p + "mlp.fc1.weight"], d, dd->ffn.f(), f, w[p + "mlp.fc1.bias"], R, f, d);
+            GemmParams g = gb(dd->h.f(), d, w.fc1_w, d, dd->ffn.f(), f, w.fc1_b, R, f, d);
             g.act = ACT_GELU_TANH;
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, gc));
         }
         {
-            GemmParams g = gb(dd->ffn.f(), f, w[p + "mlp.fc2.weight"], f, dd->x.f(), d, w[p + "mlp.fc2.bias"], R, d, f);
+            GemmParams g = gb(dd->ffn.f(), f, w.fc2_w, f, dd->x.f(), d, w.fc2_b, R, d, f);
             g.gate = mod + 5 * d; g.gate_ld = 6 * d; g.gate_rpb = T; g.R = plain_map(dd->x.f(), d);
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, gc));
         }
     }
-    const float* fm = dd->fmod.f() + (size_t)step * N * 2 * d;
     MB_TRY(ln_mod(dd->x.f(), dd->h.f(), fm, fm + d, 2 * d, T, R, d, st));
-    MB_TRY(launch_gemm(gb(dd->h.f(), d, w["final_layer.linear.weight"], d, dd->o4.f(), 4, w["final_layer.linear.bias"], R, 4, d), st));
+    MB_TRY(launch_gemm(gb(dd->h.f(), d, dd->flin_w, d, dd->o4.f(), 4, dd->flin_b, R, 4, d), st, gc));
     return 0;
 }
 
@@ -338,39 +393,113 @@ extern "C" int mb200_dit_forward_with_cfg(mb200_dit* d, const float* x, const in
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<float> tv(N);
     for (int i = 0; i < N; ++i) tv[i] = (float)t[i];
-    MB_TRY(ensure_work(d, N, T));
+    MB_TRY(ensure_work(d));
     MB_TRY(prepare_conditioning(d, tv.data(), 1, N, y, st));
-    MB_TRY(dit_forward(d, x, c, N, T, 0, 1, mask, st));
+    MB_TRY(dit_forward(d, x, c, N, T, d->mods.f(), d->fmod.f(), mask, st));     // steps == 1: the all-steps tables ARE this step's rows
     dit_cfg_out_kernel<<<(N * T + 255) / 256, 256, 0, st>>>(d->o4.f(), N, T, cfg_scale, out);
     MB_LAUNCH_CHECK();
+    ++g_launch_count;
     return 0;
 }
 
+// The 100-step loop.  Every step is the SAME captured CUDA graph (gather this step's modulation rows -> DiT forward -> in-place
+// p_sample update -> step counter + 1): one host launch per step, no host synchronisation inside the loop, no caller pointer in
+// the graph (inputs are copied into engine-owned buffers first: 4 MB, once per call).
 extern "C" int mb200_dit_sample_loop(mb200_dit* d, const float* z, const float* c, const float* y, const uint8_t* inpaint, int32_t N, int32_t T,
                                      float cfg_scale, const mb200_dit_mask* mask, const float* schedule, int32_t steps, const float* noise,
                                      float* out, void* stream) {
     MB_TRY(check_shapes(d, N, T));
     MB_REQUIRE(z && c && y && schedule && noise && out && steps >= 1, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
+    const auto& cf = d->cfg;
+    const int dm = cf.hidden;
     std::vector<float> tv((size_t)steps * N);
     for (int k = 0; k < steps; ++k)
         for (int n = 0; n < N; ++n) tv[(size_t)k * N + n] = schedule[(size_t)k * 8 + 0];
-    MB_TRY(ensure_work(d, N, T));
-    const size_t state_bytes = (size_t)N * 2 * T * 4;
-    MB_TRY(d->state0.ensure(state_bytes)); MB_TRY(d->state1.ensure(state_bytes));
+    MB_TRY(ensure_work(d));
+    const size_t total = (size_t)N * 2 * T, state_bytes = total * 4;
+    const size_t maxR = (size_t)cf.max_batch * cf.max_seq_len;
+    MB_TRY(d->state.ensure(maxR * 2 * 4)); MB_TRY(d->z_in.ensure(maxR * 2 * 4)); MB_TRY(d->c_in.ensure(maxR * cf.context_size * 4));
+    MB_TRY(d->inpaint_in.ensure(maxR * 2)); MB_TRY(d->dense_in.ensure((size_t)cf.max_seq_len * cf.max_seq_len));
+    MB_TRY(d->step_ctr.ensure(64));
+    MB_TRY(d->noise_in.ensure((size_t)steps * state_bytes));      // may grow with `steps`; graphs are dropped below when it moves
+    MB_TRY(d->sched.ensure((size_t)steps * 8 * 4));
     MB_TRY(prepare_conditioning(d, tv.data(), steps, N, y, st));
-    MB_CUDA_CHECK(cudaMemcpyAsync(d->state0.p, z, state_bytes, cudaMemcpyDeviceToDevice, st));
-    float* cur = d->state0.f();
-    float* nxt = d->state1.f();
-    const int total = N * 2 * T;
-    for (int k = 0; k < steps; ++k) {
-        MB_TRY(dit_forward(d, cur, c, N, T, k, steps, mask, st));
-        const float* s = schedule + (size_t)k * 8;
-        StepConst sc{s[1], s[2], s[3], s[4], s[5], s[6], s[7]};
-        float* dst = (k == steps - 1) ? out : nxt;
-        dit_update_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->o4.f(), cur, z, inpaint, noise + (size_t)k * total, N, T, cfg_scale, sc, dst);
-        MB_LAUNCH_CHECK();
-        std::swap(cur, nxt);
+    MB_CUDA_CHECK(cudaMemcpyAsync(d->state.p, z, state_bytes, cudaMemcpyDeviceToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(d->z_in.p, z, state_bytes, cudaMemcpyDeviceToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(d->c_in.p, c, (size_t)N * cf.context_size * T * 4, cudaMemcpyDeviceToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(d->noise_in.p, noise, (size_t)steps * state_bytes, cudaMemcpyDeviceToDevice, st));
+    if (inpaint) MB_CUDA_CHECK(cudaMemcpyAsync(d->inpaint_in.p, inpaint, total, cudaMemcpyDeviceToDevice, st));
+    mb200_dit_mask mk{MASK_NONE, 0, nullptr};
+    if (mask) {
+        mk = *mask;
+        if (mk.mask_mode == MASK_DENSE) {
+            MB_REQUIRE(mk.dense_mask != nullptr, "dense mask mode without a mask");
+            MB_CUDA_CHECK(cudaMemcpyAsync(d->dense_in.p, mk.dense_mask, (size_t)T * T, cudaMemcpyDeviceToDevice, st));
+            mk.dense_mask = reinterpret_cast<const uint8_t*>(d->dense_in.p);
+        }
     }
+    MB_CUDA_CHECK(cudaMemcpyAsync(d->sched.p, schedule, (size_t)steps * 8 * 4, cudaMemcpyHostToDevice, st));
+    MB_CUDA_CHECK(cudaMemsetAsync(d->step_ctr.p, 0, 4, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));      // `schedule` is pageable host memory of the caller
+    int* step_ptr = reinterpret_cast<int*>(d->step_ctr.p);
+    const unsigned char* ip = inpaint ? reinterpret_cast<const unsigned char*>(d->inpaint_in.p) : nullptr;
+    const int n_mods = (cf.depth * N * 6 + N * 2) * (dm / 4);
+    auto one_step = [&](cudaStream_t s) -> int {
+        dit_gather_mods_kernel<<<std::min(296, (n_mods + 255) / 256), 256, 0, s>>>(
+            reinterpret_cast<const float4*>(d->mods.p), reinterpret_cast<const float4*>(d->fmod.p), step_ptr, cf.depth, steps, N, dm / 4,
+            reinterpret_cast<float4*>(d->mods_cur.p), reinterpret_cast<float4*>(d->fmod_cur.p));
+        MB_LAUNCH_CHECK();
+        MB_TRY(dit_forward(d, d->state.f(), d->c_in.f(), N, T, d->mods_cur.f(), d->fmod_cur.f(), &mk, s));
+        dit_update_kernel<<<((int)total + 255) / 256, 256, 0, s>>>(d->o4.f(), d->state.f(), d->z_in.f(), ip, d->noise_in.f(), N, T, cfg_scale,
+                                                                  reinterpret_cast<const StepConst*>(d->sched.p), step_ptr);
+        MB_LAUNCH_CHECK();
+        dit_step_advance_kernel<<<1, 1, 0, s>>>(step_ptr);
+        MB_LAUNCH_CHECK();
+        g_launch_count += 3;
+        return 0;
+    };
+    if (!d->use_graph) {
+        for (int k = 0; k < steps; ++k) MB_TRY(one_step(st));
+    } else {
+        // the graph bakes (N, T, mask, in-paint on/off, cfg_scale, steps, the mods / noise table addresses)
+        const auto key = std::make_tuple((int)N, (int)T, (int)mk.mask_mode, (int)mk.band, (inpaint ? 1 : 0) + 2 * steps);
+        if (d->graph_cfg_scale != cfg_scale || d->graph_noise != d->noise_in.p || d->graph_mods != d->mods.p) {
+            for (auto& g : d->step_graphs) cudaGraphExecDestroy(g.second.first);
+            d->step_graphs.clear();
+            d->graph_cfg_scale = cfg_scale; d->graph_noise = d->noise_in.p; d->graph_mods = d->mods.p;
+        }
+        auto it = d->step_graphs.find(key);
+        if (it == d->step_graphs.end()) {
+            if (!d->cap_stream) MB_CUDA_CHECK(cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking));
+            cudaGraph_t graph;
+            MB_CUDA_CHECK(cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const long long before = g_launch_count;
+            const int s = one_step(d->cap_stream);
+            const cudaError_t e = cudaStreamEndCapture(d->cap_stream, &graph);
+            const long long nodes = g_launch_count - before;
+            g_launch_count = before;
+            if (s) return s;
+            MB_CUDA_CHECK(e);
+            cudaGraphExec_t exec;
+            MB_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            if (d->step_graphs.size() >= 16) {      // bounded cache
+                for (auto& g : d->step_graphs) cudaGraphExecDestroy(g.second.first);
+                d->step_graphs.clear();
+            }
+            it = d->step_graphs.emplace(key, std::make_pair(exec, nodes)).first;
+        }
+        for (int k = 0; k < steps; ++k) MB_CUDA_CHECK(cudaGraphLaunch(it->second.first, st));
+        g_launch_count += (long long)steps * it->second.second;
+    }
+    MB_CUDA_CHECK(cudaMemcpyAsync(out, d->state.p, state_bytes, cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+extern "C" int mb200_dit_set_option(mb200_dit* d, const char* name, int32_t value) {
+    MB_REQUIRE(d && name, "null argument");
+    if (!strcmp(name, "graph")) { d->use_graph = value != 0; return 0; }
+    set_last_error(std::string("unknown option ") + name);
+    return 2;
 }

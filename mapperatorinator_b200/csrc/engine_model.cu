@@ -65,21 +65,24 @@ struct mb200_model {
     DevBuf d_attn, d_ticket;            // merged attention heads [rows, d] and the per-(row, head) arrival counters of the split merge
     DevBuf g_state, g_cfg, g_vflags, g_ids, g_prefill_ids, g_keyvalid, g_leftpad, g_rowslot, g_finished, g_lastts, g_lastscores;
     int* h_flag = nullptr;              // pinned
-    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
-    std::map<std::pair<int, int>, long long> graph_nodes;   // (rows, n_splits_self) -> token-step graph
+    // graph keys carry B as well as rows: the captured sample kernel's grid is dim3(B), and a CFG call (B = 1, rows = 2) must
+    // never replay the graph of a plain batch-2 call (B = 2, rows = 2)
+    std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;
+    std::map<std::tuple<int, int, int>, long long> graph_nodes;   // (rows, B, n_splits_self) -> token-step graph
     bool use_pdl = false;
     cudaStream_t cap_stream = nullptr;
-    std::map<std::tuple<int, int, int>, int> prefill_seen;                                   // (rows, P, position rule)
-    std::map<std::tuple<int, int, int>, std::pair<cudaGraphExec_t, long long>> prefill_graphs;   // -> graph + node count
+    std::map<std::tuple<int, int, int, int>, int> prefill_seen;                                   // (rows, B, P, position rule)
+    std::map<std::tuple<int, int, int, int>, std::pair<cudaGraphExec_t, long long>> prefill_graphs;   // -> graph + node count
     // persistent megakernel path
     bool use_mega = true;
-    int num_sms = 0;
+    int num_sms = 0;                    // 0 = no cooperative launch -> no megakernel
+    int num_sms_phys = 0;
     DevBuf g_megasync;                  // [0] grid-barrier counter, [8] error flag
     DevBuf mega_trace;                  // optional per-phase clock64 stamps (option "mega_trace")
     cudaEvent_t mega_ev[2] = {nullptr, nullptr};
     double mega_ms = 0.0; long long mega_launches = 0, mega_tokens = 0;   // CUDA-event time of every megakernel launch
     std::map<std::pair<int, int>, std::pair<DevBuf*, int>> mega_phases;   // (rows, n_splits_self) -> device phase table
-    std::vector<const float*> tc_weights;  // weights with a registered tf32 lo mirror (unregistered in destroy)
+    GemmCtx gemm;                       // this engine's GEMM scratch: split-K planes, tf32 activation copies, weight mirrors, error flag
 
     int d() const { return cfg.d_model; }
     int Ts() const { return cfg.src_seq_len / 2; }
@@ -154,6 +157,7 @@ extern "C" int mb200_model_create(mb200_model** out, const mb200_model_config* c
         int dev = 0, coop = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev);
+        m->num_sms_phys = m->num_sms;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         if (!coop) m->num_sms = 0;
     }
@@ -165,7 +169,7 @@ extern "C" void mb200_model_destroy(mb200_model* m) {
     if (!m) return;
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
     for (auto& g : m->prefill_graphs) cudaGraphExecDestroy(g.second.first);
-    for (const float* w : m->tc_weights) tc_unregister_weight(w);
+    m->gemm.destroy();
     for (auto& kv : m->mega_phases) delete kv.second.first;
     for (auto& e : m->mega_ev) if (e) cudaEventDestroy(e);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
@@ -280,7 +284,7 @@ extern "C" int mb200_model_finalize(mb200_model* m) {
     // tf32 "lo" mirrors of the weights that feed large (tensor-core) GEMMs: encoder stem + layers, cross K|V projections
     {
         const long long dd = (long long)d * d;
-        auto reg = [&](const float* w, long long n) -> int { m->tc_weights.push_back(w); return tc_register_weight(w, n); };
+        auto reg = [&](const float* w, long long n) -> int { return m->gemm.register_weight(w, n); };
         MB_TRY(reg(m->emb_w, (long long)d * c.mel.n_mels));
         MB_TRY(reg(m->conv1_w, 3 * dd)); MB_TRY(reg(m->conv2_w, 3 * dd));
         for (const auto& l : m->enc) {
@@ -289,6 +293,14 @@ extern "C" int mb200_model_finalize(mb200_model* m) {
         }
         for (const auto& l : m->dec) MB_TRY(reg(l.wkv_c, 2 * dd));
         MB_CUDA_CHECK(cudaDeviceSynchronize());
+        // Scratch for the largest encoder chunk, allocated once: captured prefill graphs hold the split-K workspace pointer, so
+        // nothing in the context may move after this point.
+        const size_t chunk = (size_t)std::min(std::max(1, c.max_windows), 16);
+        const size_t a_floats = std::max({chunk * (size_t)(c.src_seq_len / 2) * f, chunk * (size_t)(c.src_seq_len + 2) * d,
+                                          chunk * (size_t)c.src_seq_len * c.mel.n_mels});
+        m->gemm.num_sms = std::max(1, m->num_sms_phys);
+        MB_TRY(m->gemm.reserve((size_t)64 << 20, a_floats * 8 + 1024));
+        m->gemm.frozen = true;
     }
 
     // ---- resident state ----
@@ -348,27 +360,27 @@ static int encode_chunk(mb200_model* m, const float* pcm, int n, int slot_begin,
     // encoder_embedder (modeling_mapperatorinator.py:433) written token-major into the zero-padded conv input
     {
         GemmParams g = gemm_base(plain_map(mel, nm), m->emb_w, nm, batched_map(embp + d, d, T2, padrow), m->emb_b, n * T2, d, nm);
-        MB_TRY(launch_gemm(g, st));
+        MB_TRY(launch_gemm(g, st, &m->gemm));
     }
     // conv1 k3 p1 + GELU  (row (b,t) of the padded buffer spans taps t-1, t, t+1 contiguously: K = 3d)
     {
         GemmParams g = gemm_base(batched_map(embp, d, T2, padrow), m->conv1_w, 3 * d, batched_map(c1p + d, d, T2, padrow), m->conv1_b,
                                  n * T2, d, 3 * d);
         g.act = ACT_GELU_ERF;
-        MB_TRY(launch_gemm(g, st));
+        MB_TRY(launch_gemm(g, st, &m->gemm));
     }
     // conv2 k3 s2 p1 + GELU + frozen positions
     {
         GemmParams g = gemm_base(batched_map(c1p, 2 * d, T, padrow), m->conv2_w, 3 * d, plain_map(x, d), m->conv2_b, n * T, d, 3 * d);
         g.act = ACT_GELU_ERF;
         g.R = batched_map(m->enc_pos, d, T, 0);
-        MB_TRY(launch_gemm(g, st));
+        MB_TRY(launch_gemm(g, st, &m->gemm));
     }
     const int rows = n * T;
     for (int l = 0; l < c.encoder_layers; ++l) {
         const LayerW& w = m->enc[l];
         MB_TRY(layernorm(x, h, w.ln1_w, w.ln1_b, rows, d, 1e-5f, st));
-        MB_TRY(launch_gemm(gemm_base(plain_map(h, d), w.wqkv, d, plain_map(qkv, 3 * d), w.bqkv, rows, 3 * d, d), st));
+        MB_TRY(launch_gemm(gemm_base(plain_map(h, d), w.wqkv, d, plain_map(qkv, 3 * d), w.bqkv, rows, 3 * d, d), st, &m->gemm));
         AttentionParams a{};
         a.q = qkv; a.q_ld = 3 * d; a.q_bs = (long long)T * 3 * d;
         a.k = qkv + d; a.k_ld = 3 * d; a.k_bs = a.q_bs;
@@ -379,18 +391,18 @@ static int encode_chunk(mb200_model* m, const float* pcm, int n, int slot_begin,
         {
             GemmParams g = gemm_base(plain_map(att, d), w.wo, d, plain_map(x, d), w.bo, rows, d, d);
             g.R = plain_map(x, d);
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, &m->gemm));
         }
         MB_TRY(layernorm(x, h, w.ln3_w, w.ln3_b, rows, d, 1e-5f, st));
         {
             GemmParams g = gemm_base(plain_map(h, d), w.fc1_w, d, plain_map(ffn, f), w.fc1_b, rows, f, d);
             g.act = ACT_GELU_ERF;
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, &m->gemm));
         }
         {
             GemmParams g = gemm_base(plain_map(ffn, f), w.fc2_w, f, plain_map(x, d), w.fc2_b, rows, d, f);
             g.R = plain_map(x, d);
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, &m->gemm));
         }
     }
     float* enc = enc_out ? enc_out : h;
@@ -398,7 +410,7 @@ static int encode_chunk(mb200_model* m, const float* pcm, int n, int slot_begin,
     // cross-attention K|V of every decoder layer, straight into the resident slots
     for (int l = 0; l < c.decoder_layers; ++l) {
         float* dst = m->cross_kv.as<float>() + (size_t)l * m->cross_layer_stride() + (size_t)slot_begin * T * 2 * d;
-        MB_TRY(launch_gemm(gemm_base(plain_map(enc, d), m->dec[l].wkv_c, d, plain_map(dst, 2 * d), m->dec[l].bkv_c, rows, 2 * d, d), st));
+        MB_TRY(launch_gemm(gemm_base(plain_map(enc, d), m->dec[l].wkv_c, d, plain_map(dst, 2 * d), m->dec[l].bkv_c, rows, 2 * d, d), st, &m->gemm));
     }
     return 0;
 }
@@ -450,9 +462,9 @@ static int decoder_prefill(mb200_model* m, int rows, int P, const long long* ids
         float* skv = m->self_kv.as<float>() + (size_t)l * m->self_layer_stride();
         const float* ckv = m->cross_kv.as<float>() + (size_t)l * m->cross_layer_stride();
         MB_TRY(layernorm(x, h, w.ln1_w, w.ln1_b, (int)RP, d, 1e-5f, st));
-        MB_TRY(launch_gemm(gemm_base(plain_map(h, d), w.wqkv, d, plain_map(q, d), w.bqkv, (int)RP, d, d), st));
+        MB_TRY(launch_gemm(gemm_base(plain_map(h, d), w.wqkv, d, plain_map(q, d), w.bqkv, (int)RP, d, d), st, &m->gemm));
         MB_TRY(launch_gemm(gemm_base(plain_map(h, d), w.wqkv + (size_t)d * d, d, batched_map(skv, 2 * d, P, self_row), w.bqkv + d, (int)RP,
-                                     2 * d, d), st));
+                                     2 * d, d), st, &m->gemm));
         AttentionParams a{};
         a.q = q; a.q_ld = d; a.q_bs = (long long)P * d;
         a.k = skv; a.k_ld = 2 * d; a.k_bs = self_row;
@@ -464,10 +476,10 @@ static int decoder_prefill(mb200_model* m, int rows, int P, const long long* ids
         {
             GemmParams g = gemm_base(plain_map(att, d), w.wo, d, plain_map(x, d), w.bo, (int)RP, d, d);
             g.R = plain_map(x, d);
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, &m->gemm));
         }
         MB_TRY(layernorm(x, h, w.ln2_w, w.ln2_b, (int)RP, d, 1e-5f, st));
-        MB_TRY(launch_gemm(gemm_base(plain_map(h, d), w.wq_c, d, plain_map(q, d), w.bq_c, (int)RP, d, d), st));
+        MB_TRY(launch_gemm(gemm_base(plain_map(h, d), w.wq_c, d, plain_map(q, d), w.bq_c, (int)RP, d, d), st, &m->gemm));
         AttentionParams ca{};
         ca.q = q; ca.q_ld = d; ca.q_bs = (long long)P * d;
         ca.k = ckv; ca.k_ld = 2 * d; ca.k_bs = (long long)T * 2 * d;
@@ -478,18 +490,18 @@ static int decoder_prefill(mb200_model* m, int rows, int P, const long long* ids
         {
             GemmParams g = gemm_base(plain_map(att, d), w.wo_c, d, plain_map(x, d), w.bo_c, (int)RP, d, d);
             g.R = plain_map(x, d);
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, &m->gemm));
         }
         MB_TRY(layernorm(x, h, w.ln3_w, w.ln3_b, (int)RP, d, 1e-5f, st));
         {
             GemmParams g = gemm_base(plain_map(h, d), w.fc1_w, d, plain_map(ffn, f), w.fc1_b, (int)RP, f, d);
             g.act = ACT_GELU_ERF;
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, &m->gemm));
         }
         {
             GemmParams g = gemm_base(plain_map(ffn, f), w.fc2_w, f, plain_map(x, d), w.fc2_b, (int)RP, d, f);
             g.R = plain_map(x, d);
-            MB_TRY(launch_gemm(g, st));
+            MB_TRY(launch_gemm(g, st, &m->gemm));
         }
     }
     return 0;
@@ -761,7 +773,7 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
             MB_TRY(launch_sample(sample_params(m, rows), B, s, false));
             return 0;
         };
-        const auto pkey = std::make_tuple(rows, (int)P, (int)gp->position_rule);
+        const auto pkey = std::make_tuple(rows, (int)B, (int)P, (int)gp->position_rule);
         auto seen = m->prefill_seen.find(pkey);
         if (seen == m->prefill_seen.end()) {
             m->prefill_seen[pkey] = 1;
@@ -783,6 +795,11 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
                 cudaGraphExec_t exec;
                 MB_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
                 cudaGraphDestroy(graph);
+                if (m->prefill_graphs.size() >= 48) {      // bounded cache: real songs see many prompt lengths; drop everything and re-learn
+                    for (auto& g : m->prefill_graphs) cudaGraphExecDestroy(g.second.first);
+                    m->prefill_graphs.clear();
+                    m->prefill_seen.clear();
+                }
                 git = m->prefill_graphs.emplace(pkey, std::make_pair(exec, nodes)).first;
             }
             MB_CUDA_CHECK(cudaGraphLaunch(git->second.first, st));
@@ -802,7 +819,7 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
         return 0;
     }
     // ---- token loop, graph path: one graph replay per token, flag polled every few tokens ----
-    auto key = std::make_pair(rows, n_splits_self);
+    auto key = std::make_tuple(rows, (int)B, n_splits_self);
     auto it = m->graphs.find(key);
     if (it == m->graphs.end()) {
         // capture on an engine-owned stream (the caller's stream may be the legacy default stream, which cannot capture)
@@ -876,7 +893,7 @@ extern "C" int mb200_model_forward_logits(mb200_model* m, const int32_t* slots, 
     const int R = B * len;
     MB_TRY(layernorm(m->p_x.as<float>(), m->p_h.as<float>(), m->dec_ln_w, m->dec_ln_b, R, d, 1e-5f, st));
     MB_TRY(launch_gemm(gemm_base(plain_map(m->p_h.as<float>(), d), m->proj_out, d, plain_map(logits_out, c.vocab_size_out), nullptr, R,
-                                 c.vocab_size_out, d), st));
+                                 c.vocab_size_out, d), st, &m->gemm));
     return 0;
 }
 

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_kernel(GemmParams p) {
     for (int h = 0; h < 2; ++h) {
         long long m = m0 + lrow + h * 64;
         a_ok[h] = m < p.M;
-        a_ptr[h] = a_ok[h] ? p.A.row(m) : p.A.ptr;
+        a_ptr[h] = a_ok[h] ? p.A.row(p.m_base + m) : p.A.ptr;
         int n = n0 + lrow + h * 64;
         w_ok[h] = n < p.N;
         w_ptr[h] = p.W + (long long)(w_ok[h] ? n : 0) * p.ldw;
@@ -116,9 +116,9 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_kernel(GemmParams p) {
     for (int i = 0; i < 8; ++i) {
         long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (m >= p.M) continue;
-        float* crow = p.C.row(m);
-        const float* rrow = p.R.ptr ? p.R.row(m) : nullptr;
-        const float* grow = p.gate ? p.gate + (m / p.gate_rpb) * p.gate_ld : nullptr;
+        float* crow = p.C.row(p.m_base + m);
+        const float* rrow = p.R.ptr ? p.R.row(p.m_base + m) : nullptr;
+        const float* grow = p.gate ? p.gate + ((p.m_base + m) / p.gate_rpb) * p.gate_ld : nullptr;
 #pragma unroll
         for (int jh = 0; jh < 2; ++jh) {
             int n = n0 + jh * 64 + tx * 4;
@@ -142,95 +142,74 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(GemmParams p) {
     if (idx >= (long long)p.M * p.N) return;
     const long long m = idx / p.N;
     const int n = (int)(idx - m * p.N);
-    float v = 0.f;
-    for (int z = 0; z < p.splitk; ++z) v += p.splitk_ws[((long long)z * p.M + m) * p.N + n];   // fixed order
+    float v = p.splitk_ws[m * p.N + n];
+    for (int z = 1; z < p.splitk; ++z) v += p.splitk_ws[((long long)z * p.M + m) * p.N + n];   // fixed order: ((p0 + p1) + p2) + ...
     if (p.bias) v += __ldg(p.bias + n);
     v = apply_act(v, p.act) * p.alpha;
-    if (p.gate) v *= __ldg(p.gate + (m / p.gate_rpb) * p.gate_ld + n);
-    if (p.R.ptr) v += p.R.row(m)[n];
-    p.C.row(m)[n] = v;
-}
-
-// ---- skinny variant: M <= 64 rows (decoder prefill of a 17-50 token prompt) ------------------------------------------------
-// The 128x128 tile kernel above would run such a problem on N/128 = 6..24 CTAs with a latency-bound K loop (measured 115 us
-// per projection, 11.5 ms per prefill).  Here the weight matrix is the streamed operand: one CTA owns 16 weight rows, lanes
-// own the (<= 64) activation rows, the activation chunk sits transposed in shared memory and every weight value is a
-// shared-memory broadcast.  No cross-lane reduction; fixed k order.
-constexpr int SK_ROWS = 16, SK_KC = 128, SK_MPAD = 65;
-
-__global__ void __launch_bounds__(128) gemm_skinny_kernel(GemmParams p) {
-    __shared__ float xT[SK_KC][SK_MPAD];                 // [k][m], padded: conflict-free transposed stores
-    __shared__ __align__(16) float ws[SK_ROWS][SK_KC];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n0 = blockIdx.x * SK_ROWS;
-    float acc[2][4];
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[h][r] = 0.f;
-
-    for (int k0 = 0; k0 < p.K; k0 += SK_KC) {
-        const int kc = min(SK_KC, p.K - k0);             // multiple of 4
-        for (int idx = tid; idx < 64 * (SK_KC / 4); idx += 128) {
-            const int m = idx / (SK_KC / 4), kq = (idx - m * (SK_KC / 4)) * 4;
-            float4 v = make_float4(0, 0, 0, 0);
-            if (m < p.M && kq < kc) v = __ldg(reinterpret_cast<const float4*>(p.A.row(m) + k0 + kq));
-            xT[kq + 0][m] = v.x; xT[kq + 1][m] = v.y; xT[kq + 2][m] = v.z; xT[kq + 3][m] = v.w;
-        }
-        for (int idx = tid; idx < SK_ROWS * (SK_KC / 4); idx += 128) {
-            const int r = idx / (SK_KC / 4), kq = (idx - r * (SK_KC / 4)) * 4;
-            float4 v = make_float4(0, 0, 0, 0);
-            if (n0 + r < p.N && kq < kc) v = __ldg(reinterpret_cast<const float4*>(p.W + (long long)(n0 + r) * p.ldw + k0 + kq));
-            *reinterpret_cast<float4*>(&ws[r][kq]) = v;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int kk = 0; kk < SK_KC; kk += 4) {
-            float4 w4[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) w4[r] = *reinterpret_cast<const float4*>(&ws[warp * 4 + r][kk]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float x0 = xT[kk + j][lane], x1 = xT[kk + j][lane + 32];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float wv = j == 0 ? w4[r].x : (j == 1 ? w4[r].y : (j == 2 ? w4[r].z : w4[r].w));
-                    acc[0][r] = fmaf(wv, x0, acc[0][r]);
-                    acc[1][r] = fmaf(wv, x1, acc[1][r]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int m = lane + 32 * h;
-        if (m >= p.M) continue;
-        float* crow = p.C.row(m);
-        const float* rrow = p.R.ptr ? p.R.row(m) : nullptr;
-        const float* grow = p.gate ? p.gate + (m / p.gate_rpb) * p.gate_ld : nullptr;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int n = n0 + warp * 4 + r;
-            if (n >= p.N) continue;
-            float v = acc[h][r];
-            if (p.bias) v += __ldg(p.bias + n);
-            v = apply_act(v, p.act) * p.alpha;
-            if (grow) v *= __ldg(grow + n);
-            if (rrow) v += rrow[n];
-            crow[n] = v;
-        }
-    }
+    if (p.gate) v *= __ldg(p.gate + ((p.m_base + m) / p.gate_rpb) * p.gate_ld + n);
+    if (p.R.ptr) v += p.R.row(p.m_base + m)[n];
+    p.C.row(p.m_base + m)[n] = v;
 }
 
 }  // namespace
 
-// fixed-size split-K workspace, allocated once (captured graphs hold this pointer); null if `need` does not fit
-float* splitk_workspace(size_t need) {
-    static float* ws = nullptr;
-    static const size_t ws_bytes = (size_t)64 << 20;
-    if (!ws && cudaMalloc(&ws, ws_bytes) != cudaSuccess) { ws = nullptr; return nullptr; }
-    return need <= ws_bytes ? ws : nullptr;
+// ---- per-engine scratch ------------------------------------------------------------------------------------------------
+int GemmCtx::reserve(size_t splitk_need, size_t a_split_need) {
+    auto grow = [&](float*& ptr, size_t& have, size_t need) -> int {
+        if (need <= have) return 0;
+        MB_REQUIRE(!frozen, "GEMM scratch is referenced by a captured CUDA graph and cannot grow (reserve the largest shape before capturing)");
+        if (ptr) MB_CUDA_CHECK(cudaFree(ptr));
+        ptr = nullptr; have = 0;
+        MB_CUDA_CHECK(cudaMalloc(&ptr, need));
+        have = need;
+        return 0;
+    };
+    int s = grow(splitk_ws, splitk_bytes, splitk_need);
+    if (s) return s;
+    s = grow(a_split, a_split_bytes, a_split_need);
+    if (s) return s;
+    if (!tc_err) { MB_CUDA_CHECK(cudaMalloc(&tc_err, 4)); MB_CUDA_CHECK(cudaMemset(tc_err, 0, 4)); }
+    return 0;
+}
+
+int GemmCtx::error() {
+    if (!tc_err) return 0;
+    int h = 0;
+    cudaMemcpy(&h, tc_err, 4, cudaMemcpyDeviceToHost);
+    return h;
+}
+
+void GemmCtx::destroy() {
+    for (auto& kv : mirrors) cudaFree(const_cast<float*>(kv.second.hi));      // hi and lo share one allocation
+    mirrors.clear();
+    if (splitk_ws) cudaFree(splitk_ws);
+    if (a_split) cudaFree(a_split);
+    if (tc_err) cudaFree(tc_err);
+    splitk_ws = a_split = nullptr; tc_err = nullptr; splitk_bytes = a_split_bytes = 0; frozen = false;
+}
+
+GemmCtx* default_gemm_ctx() {
+    static GemmCtx ctx;
+    static bool init = false;
+    if (!init) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&ctx.num_sms, cudaDevAttrMultiProcessorCount, dev);
+        init = true;
+    }
+    return &ctx;
+}
+
+// S of an (N, K) problem on the SIMT path: the split that fills the machine when M is one 128-row tile (decoder prefill, DiT
+// conditioning) — chosen from N and K only, so a row's sum does not depend on how many rows share the launch.
+int gemm_splits_simt(int N, int K, int num_sms, int* k_per_split) {
+    const int tiles_n = (N + BN - 1) / BN;
+    int splits = 1;
+    if (tiles_n * 2 <= num_sms && K >= 64) splits = std::max(1, std::min((num_sms + tiles_n - 1) / tiles_n, K / 32));
+    const int kps = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+    splits = (K + kps - 1) / kps;
+    *k_per_split = kps;
+    return splits;
 }
 
 int launch_splitk_reduce(const GemmParams& q, cudaStream_t stream) {
@@ -240,42 +219,43 @@ int launch_splitk_reduce(const GemmParams& q, cudaStream_t stream) {
     return 0;
 }
 
-int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+int launch_gemm(const GemmParams& p, cudaStream_t stream, GemmCtx* ctx) {
+    MB_REQUIRE(ctx != nullptr, "GEMM needs its engine's scratch context");
     MB_REQUIRE(p.K % 4 == 0, "GEMM K must be a multiple of 4 (float4 loads)");
     MB_REQUIRE(p.A.ld % 4 == 0 && p.ldw % 4 == 0, "GEMM operand row strides must be multiples of 4 floats");
     MB_REQUIRE((reinterpret_cast<uintptr_t>(p.A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0,
                "GEMM operands must be 16-byte aligned");
     if (p.M <= 0 || p.N <= 0) return 0;
-    if (tc_gemm_eligible(p) && launch_gemm_tc(p, stream) == 0) return 0;      // tensor cores (3xTF32); falls through on failure
-    static const int small_m_mode = [] { const char* e = getenv("MB200_SMALLM"); return e ? atoi(e) : 2; }();   // 0 tile, 1 skinny, 2 split-K
-    if (p.M <= 64 && small_m_mode == 1) {
-        gemm_skinny_kernel<<<(p.N + SK_ROWS - 1) / SK_ROWS, 128, 0, stream>>>(p);
+    if (tc_gemm_eligible(p, ctx)) return launch_gemm_tc(p, stream, ctx);      // tensor cores (3xTF32)
+    int kps = 0;
+    const int splits = gemm_splits_simt(p.N, p.K, ctx->num_sms, &kps);
+    const int tiles_n = (p.N + BN - 1) / BN;
+    if (splits == 1) {
+        dim3 grid(tiles_n, (unsigned)((p.M + BM - 1) / BM));
+        gemm_f32_kernel<<<grid, 256, 0, stream>>>(p);
         MB_LAUNCH_CHECK();
         ++g_launch_count;
         return 0;
     }
-    const int tiles_m = (int)((p.M + BM - 1) / BM), tiles_n = (p.N + BN - 1) / BN;
-    if ((long long)tiles_m * tiles_n < 100 && small_m_mode == 2 && p.K >= 64) {
-        // fewer output tiles than SMs (decoder prefill, a single encoder window, DiT conditioning): split K over enough CTAs to
-        // fill the machine — these problems are weight-streaming bound, not FLOP bound
-        const int tiles = tiles_m * tiles_n;
-        int splits = std::max(1, std::min((148 + tiles - 1) / tiles, p.K / 32));
-        const int kps = ((p.K + splits - 1) / splits + BK - 1) / BK * BK;
-        splits = (p.K + kps - 1) / kps;
-        float* ws = splits > 1 ? splitk_workspace((size_t)splits * p.M * p.N * sizeof(float)) : nullptr;
-        if (ws) {
-            GemmParams q = p;
-            q.splitk_ws = ws; q.splitk = splits; q.k_per_split = kps;
-            gemm_f32_kernel<<<dim3(tiles_n, tiles_m, splits), 256, 0, stream>>>(q);
-            MB_LAUNCH_CHECK();
-            ++g_launch_count;
-            return launch_splitk_reduce(q, stream);
-        }
+    // grid split; rows are processed in slices whose S partial planes fit the workspace (slicing M does not touch the arithmetic)
+    const size_t row_bytes = (size_t)splits * p.N * sizeof(float);
+    if (row_bytes * (size_t)p.M > ctx->splitk_bytes && !ctx->frozen) {
+        const int s = ctx->reserve(std::max(row_bytes * (size_t)std::min(p.M, 2048), (size_t)64 << 20), 0);
+        if (s) return s;
     }
-    dim3 grid((p.N + BN - 1) / BN, (unsigned)((p.M + BM - 1) / BM));
-    gemm_f32_kernel<<<grid, 256, 0, stream>>>(p);
-    MB_LAUNCH_CHECK();
-    ++g_launch_count;
+    MB_REQUIRE(ctx->splitk_bytes >= row_bytes * BM, "split-K workspace smaller than one row tile");
+    const long long rows_per_pass = std::min<long long>(p.M, (long long)(ctx->splitk_bytes / row_bytes) / BM * BM);
+    for (long long m0 = 0; m0 < p.M; m0 += rows_per_pass) {
+        GemmParams q = p;
+        q.m_base = p.m_base + m0;
+        q.M = (int)std::min<long long>(rows_per_pass, p.M - m0);
+        q.splitk_ws = ctx->splitk_ws; q.splitk = splits; q.k_per_split = kps; q.split_mode = 1;
+        gemm_f32_kernel<<<dim3(tiles_n, (unsigned)((q.M + BM - 1) / BM), splits), 256, 0, stream>>>(q);
+        MB_LAUNCH_CHECK();
+        ++g_launch_count;
+        const int s = launch_splitk_reduce(q, stream);
+        if (s) return s;
+    }
     return 0;
 }
 

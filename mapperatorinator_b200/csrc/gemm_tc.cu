@@ -30,8 +30,6 @@
 
 namespace mb200 {
 
-struct Tf32Mirror { const float* hi; const float* lo; };
-std::unordered_map<const float*, Tf32Mirror> g_w_lo;   // weight matrix -> its tf32 hi / lo arrays (filled by the engines at finalize)
 int g_tc_enabled = 1;
 
 namespace {
@@ -81,6 +79,18 @@ __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"l"(__cvta_generic_to_shared(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(unsigned (&v)[32], unsigned taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
                    const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo, GemmParams p, int a_rpb, int* err) {
@@ -91,9 +101,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int n0 = blockIdx.x * TC_BN;
     const long long m0 = (long long)blockIdx.y * TC_BM;
     const int nkb_all = (p.K + TC_BK - 1) / TC_BK;
-    // split-K (under-filled grids): CTA z owns k-blocks [kb0, kb0 + nkb) and stores raw partial sums; gemm.cu's reduce kernel finishes
-    const int kb0 = p.splitk > 1 ? blockIdx.z * (p.k_per_split / TC_BK) : 0;
-    const int nkb = p.splitk > 1 ? max(0, min(nkb_all - kb0, p.k_per_split / TC_BK)) : nkb_all;
+    // Split-K (kernels.h): k-range z = k-blocks [z*kpb, (z+1)*kpb) is summed on its own.  Grid split (under-filled grids): CTA
+    // blockIdx.z owns range z and stores raw partials, gemm.cu's reduce kernel adds them in order.  In-tile split (large M): this CTA
+    // walks every range, range z accumulating into TMEM columns [z*128, z*128+128); the epilogue adds the S accumulators in the same
+    // order.  Same partial sums, same additions, same bits.
+    const int kpb = p.splitk > 1 ? p.k_per_split / TC_BK : nkb_all;
+    const bool grid_split = p.split_mode == 1, tile_split = p.split_mode == 2;
+    const int kb0 = grid_split ? blockIdx.z * kpb : 0;
+    const int nkb = grid_split ? max(0, min(nkb_all - kb0, kpb)) : nkb_all;
+    const int nacc = tile_split ? p.splitk : 1;
+    const unsigned tmem_cols = nacc == 1 ? 128u : (nacc == 2 ? 256u : 512u);
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -104,7 +121,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&bars->tmem_base)), "r"(128) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -146,14 +163,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned base = s32(smem + s * TC_STAGE_BYTES);
+                const int z = tile_split ? kb / kpb : 0, kr = tile_split ? kb - z * kpb : kb;      // accumulator and position inside its k-range
+                const unsigned acc = tmem + (unsigned)(z * TC_BN);
 #pragma unroll
                 for (int sub = 0; sub < TC_BK / 8; ++sub) {
                     const unsigned off = sub * 32;       // 8 tf32 = 32 bytes along K inside the 128-byte swizzle atom
                     const unsigned long long a_hi = umma_desc(base + off), a_lo = umma_desc(base + TC_TILE_BYTES + off);
                     const unsigned long long w_hi = umma_desc(base + 2 * TC_TILE_BYTES + off), w_lo = umma_desc(base + 3 * TC_TILE_BYTES + off);
-                    umma_tf32(tmem, a_hi, w_hi, idesc, (kb > 0 || sub > 0) ? 1u : 0u);
-                    umma_tf32(tmem, a_hi, w_lo, idesc, 1u);
-                    umma_tf32(tmem, a_lo, w_hi, idesc, 1u);
+                    umma_tf32(acc, a_hi, w_hi, idesc, (kr > 0 || sub > 0) ? 1u : 0u);
+                    umma_tf32(acc, a_hi, w_lo, idesc, 1u);
+                    umma_tf32(acc, a_lo, w_hi, idesc, 1u);
                 }
                 umma_commit(&bars->empty[s]);            // frees the stage once these MMAs have read it
             }
@@ -175,7 +194,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const long long m = m0 + lg * 32 + lane;
             RowPtrs rp{nullptr, nullptr, nullptr};
             if (ok && m < p.M) {
-                if (p.splitk > 1) {
+                if (grid_split) {
                     rp.c = p.splitk_ws + ((long long)blockIdx.z * p.M + m) * p.N;         // raw partial sums of this split
                 } else {
                     rp.c = p.C.row(m);
@@ -190,15 +209,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
             unsigned v[32];
             const unsigned taddr = tmem + ((unsigned)(lg * 32) << 16) + (unsigned)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-                "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld32(v, taddr);
+            for (int z = 1; z < nacc; ++z) {                                              // in-tile split: ((acc0 + acc1) + acc2) + acc3
+                unsigned w[32];
+                tmem_ld32(w, taddr + (unsigned)(z * TC_BN));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);     // bank (lane + j) % 32: conflict-free
             __syncwarp();
@@ -210,7 +227,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const RowPtrs rp = rows[rr];                                              // broadcast
                 if (rp.c && n_ok) {
                     float x = stg[rr * 33 + lane];
-                    if (p.splitk > 1) { rp.c[n] = x; continue; }
+                    if (grid_split) { rp.c[n] = x; continue; }
                     if (p.bias) x += bias_v;
                     x = apply_act(x, p.act) * p.alpha;
                     if (rp.g) x *= __ldg(rp.g + n);
@@ -223,7 +240,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
 }
 
 // x = hi + lo with hi = round-to-nearest tf32(x) and lo = round-to-nearest tf32(x - hi).  Rounding (not truncating) both parts
@@ -274,80 +291,105 @@ int make_map(CUtensorMap* out, const float* base, long long K, long long rows_pe
     return 0;
 }
 
-float* g_alo = nullptr;          // activation "lo" scratch (same layout as the A buffer it mirrors)
-size_t g_alo_bytes = 0;
-int* g_tc_err = nullptr;
-
 }  // namespace
 
-// One-time self test of the tensor-core path against a host fp64 product.  If the tcgen05 pipeline misbehaves on this
-// driver / device the path is switched off LOUDLY and every GEMM stays on the fp32 SIMT kernel (same results, slower).
+// S of an (N, K) problem on the tensor-core path: the split that fills the machine for ONE encoder window (M = 512 rows = 4 row
+// tiles), at least 8 k-blocks per range, at most 4 ranges (4 x 128 TMEM columns).  A function of N and K only.
+int gemm_splits_tc(int N, int K, int num_sms, int* k_per_split) {
+    const int tiles_ref = 4 * ((N + TC_BN - 1) / TC_BN), nkb = (K + TC_BK - 1) / TC_BK;
+    int splits = std::max(1, std::min({4, num_sms / std::max(1, tiles_ref), nkb / 8}));
+    const int kpb = (nkb + splits - 1) / splits;                  // k-blocks per range
+    splits = (nkb + kpb - 1) / kpb;                               // no empty range
+    *k_per_split = kpb * TC_BK;
+    return splits;
+}
+
+// One-time self test of the tensor-core path against a host fp64 product (grid split, in-tile split and unsplit shapes).  If the
+// tcgen05 pipeline misbehaves on this driver / device the path is switched off LOUDLY and every GEMM stays on the fp32 SIMT kernel.
 static int g_tc_tested = 0;
 static void tc_self_test() {
     g_tc_tested = 1;
-    const int M = 512, N = 128, K = 96;
-    std::vector<float> a((size_t)M * K), w((size_t)N * K), c((size_t)M * N);
-    unsigned s = 12345u;
-    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)((s >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
-    for (auto& v : a) v = rnd();
-    for (auto& v : w) v = rnd();
-    float *da = nullptr, *dw = nullptr, *dc = nullptr;
-    bool ok = cudaMalloc(&da, a.size() * 4) == cudaSuccess && cudaMalloc(&dw, w.size() * 4) == cudaSuccess && cudaMalloc(&dc, c.size() * 4) == cudaSuccess;
-    if (ok) {
-        cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
-        GemmParams g{};
-        g.A = plain_map(da, K); g.W = dw; g.ldw = K; g.C = plain_map(dc, N); g.alpha = 1.f; g.gate_rpb = 1; g.M = M; g.N = N; g.K = K;
-        ok = tc_register_weight(dw, (long long)N * K) == 0 && launch_gemm_tc(g, nullptr) == 0 && cudaDeviceSynchronize() == cudaSuccess &&
-             tc_gemm_error() == 0;
+    GemmCtx ctx;
+    ctx.num_sms = default_gemm_ctx()->num_sms;
+    bool all_ok = true;
+    const int shapes[3][3] = {{512, 128, 96}, {512, 128, 1024}, {2048, 256, 1024}};      // unsplit, grid split, in-tile split
+    for (int t = 0; t < 3 && all_ok; ++t) {
+        const int M = shapes[t][0], N = shapes[t][1], K = shapes[t][2];
+        std::vector<float> a((size_t)M * K), w((size_t)N * K), c((size_t)M * N);
+        unsigned s = 12345u + t;
+        auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)((s >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+        for (auto& v : a) v = rnd();
+        for (auto& v : w) v = rnd();
+        float *da = nullptr, *dw = nullptr, *dc = nullptr;
+        bool ok = cudaMalloc(&da, a.size() * 4) == cudaSuccess && cudaMalloc(&dw, w.size() * 4) == cudaSuccess && cudaMalloc(&dc, c.size() * 4) == cudaSuccess;
         if (ok) {
-            cudaMemcpy(c.data(), dc, c.size() * 4, cudaMemcpyDeviceToHost);
-            double worst = 0;
-            for (int m = 0; m < M; m += 37)
-                for (int n = 0; n < N; n += 5) {
-                    double r = 0;
-                    for (int k = 0; k < K; ++k) r += (double)a[(size_t)m * K + k] * (double)w[(size_t)n * K + k];
-                    worst = std::max(worst, std::fabs(r - (double)c[(size_t)m * N + n]));
-                }
-            ok = worst < 1e-4;
+            cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
+            GemmParams g{};
+            g.A = plain_map(da, K); g.W = dw; g.ldw = K; g.C = plain_map(dc, N); g.alpha = 1.f; g.gate_rpb = 1; g.M = M; g.N = N; g.K = K;
+            ok = ctx.register_weight(dw, (long long)N * K) == 0 && launch_gemm_tc(g, nullptr, &ctx) == 0 && cudaDeviceSynchronize() == cudaSuccess &&
+                 ctx.error() == 0;
+            if (ok) {
+                cudaMemcpy(c.data(), dc, c.size() * 4, cudaMemcpyDeviceToHost);
+                double worst = 0;
+                for (int m = 0; m < M; m += 37)
+                    for (int n = 0; n < N; n += 5) {
+                        double r = 0;
+                        for (int k = 0; k < K; ++k) r += (double)a[(size_t)m * K + k] * (double)w[(size_t)n * K + k];
+                        worst = std::max(worst, std::fabs(r - (double)c[(size_t)m * N + n]));
+                    }
+                ok = worst < 1e-3;
+            }
         }
+        if (da) cudaFree(da);
+        if (dw) cudaFree(dw);
+        if (dc) cudaFree(dc);
+        all_ok = all_ok && ok;
     }
-    if (da) cudaFree(da);
-    if (dw) { tc_unregister_weight(dw); cudaFree(dw); }
-    if (dc) cudaFree(dc);
-    if (!ok) {
+    ctx.destroy();
+    if (!all_ok) {
         g_tc_enabled = 0;
         fprintf(stderr, "[mapperatorinator_b200] WARNING: tcgen05 GEMM self-test FAILED — tensor-core path disabled, using the fp32 SIMT GEMM\n");
         cudaGetLastError();
     }
 }
 
-bool tc_gemm_eligible(const GemmParams& p) {
+bool tc_gemm_eligible(const GemmParams& p, GemmCtx* ctx) {
     if (g_tc_enabled && !g_tc_tested) tc_self_test();
-    if (!g_tc_enabled || p.splitk > 1) return false;
+    if (!g_tc_enabled || p.m_base != 0) return false;
     if (p.M < 512 || p.N < 64 || p.K < 32 || p.K % 4 != 0) return false;
-    if (g_w_lo.find(p.W) == g_w_lo.end()) return false;
+    if (ctx->mirrors.find(p.W) == ctx->mirrors.end()) return false;
     if (p.A.rpb != 0 && (p.A.rpb % TC_BM) != 0) return false;
     if ((reinterpret_cast<uintptr_t>(p.A.ptr) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15) || (p.A.ld % 4) || (p.ldw % 4)) return false;
     if (p.A.rpb != 0 && (p.A.bstride % 4)) return false;
     return true;
 }
 
-int launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
-    const Tf32Mirror wm = g_w_lo.at(p.W);
+int launch_gemm_tc(const GemmParams& p, cudaStream_t stream, GemmCtx* ctx) {
+    const Tf32Mirror wm = ctx->mirrors.at(p.W);
     // extent of the buffer A rows live in (rows may overlap: im2col-free conv) and its lo mirror
     const long long batches = p.A.rpb ? (p.M + p.A.rpb - 1) / p.A.rpb : 1;
     const long long rpb = p.A.rpb ? p.A.rpb : p.M;
     const long long extent = (batches - 1) * (p.A.rpb ? p.A.bstride : 0) + (rpb - 1) * p.A.ld + p.K;
     const long long n4 = (extent + 3) / 4;
-    if ((size_t)n4 * 32 > g_alo_bytes) {       // hi and lo halves
-        if (g_alo) cudaFree(g_alo);
-        g_alo_bytes = std::max((size_t)n4 * 32, (size_t)512 << 20);
-        MB_CUDA_CHECK(cudaMalloc(&g_alo, g_alo_bytes));
+    dim3 grid((p.N + TC_BN - 1) / TC_BN, (unsigned)((p.M + TC_BM - 1) / TC_BM));
+    GemmParams q = p;
+    q.splitk = gemm_splits_tc(p.N, p.K, ctx->num_sms, &q.k_per_split);
+    q.split_mode = 0; q.splitk_ws = nullptr;
+    if (q.splitk > 1) {
+        // grid split while the tiles alone would leave SMs idle, in-tile split otherwise: same bits either way
+        const int tiles = (int)(grid.x * grid.y);
+        q.split_mode = tiles * 4 <= ctx->num_sms * 3 ? 1 : 2;
+    } else {
+        q.splitk = 1;
     }
-    float* a_hi = g_alo;
-    float* a_lo = g_alo + n4 * 4;
-    if (!g_tc_err) { MB_CUDA_CHECK(cudaMalloc(&g_tc_err, 4)); MB_CUDA_CHECK(cudaMemset(g_tc_err, 0, 4)); }
+    {
+        const int s = ctx->reserve(q.split_mode == 1 ? (size_t)q.splitk * p.M * p.N * sizeof(float) : 0, (size_t)n4 * 32);      // hi and lo halves
+        if (s) return s;
+    }
+    if (q.split_mode == 1) { q.splitk_ws = ctx->splitk_ws; grid.z = q.splitk; }
+    float* a_hi = ctx->a_split;
+    float* a_lo = ctx->a_split + n4 * 4;
     tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(p.A.ptr, a_hi, a_lo, n4);
     MB_LAUNCH_CHECK();
     CUtensorMap ma, mal, mw, mwl;
@@ -361,55 +403,29 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
         MB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    dim3 grid((p.N + TC_BN - 1) / TC_BN, (unsigned)((p.M + TC_BM - 1) / TC_BM));
-    // Under-filled grids (a single encoder window: 24-72 tiles on 148 SMs) split K so every SM gets a tile; each split keeps at
-    // least 8 k-blocks.  Fixed split -> fixed summation order.
-    const int tiles = (int)(grid.x * grid.y), nkb = (p.K + TC_BK - 1) / TC_BK;
-    int splits = std::min({4, 148 / std::max(1, tiles), nkb / 8});
-    if (splits > 1) {
-        const int kpb = (nkb + splits - 1) / splits;                  // k-blocks per split
-        splits = (nkb + kpb - 1) / kpb;                               // no empty split
-        float* ws = splits > 1 ? splitk_workspace((size_t)splits * p.M * p.N * sizeof(float)) : nullptr;
-        if (ws) {
-            GemmParams q = p;
-            q.splitk_ws = ws; q.splitk = splits; q.k_per_split = kpb * TC_BK;
-            grid.z = splits;
-            gemm_tf32x3_kernel<<<grid, TC_THREADS, smem, stream>>>(ma, mal, mw, mwl, q, p.A.rpb, g_tc_err);
-            MB_LAUNCH_CHECK();
-            g_launch_count += 2;
-            return launch_splitk_reduce(q, stream);
-        }
-    }
-    gemm_tf32x3_kernel<<<grid, TC_THREADS, smem, stream>>>(ma, mal, mw, mwl, p, p.A.rpb, g_tc_err);
+    gemm_tf32x3_kernel<<<grid, TC_THREADS, smem, stream>>>(ma, mal, mw, mwl, q, p.A.rpb, ctx->tc_err);
     MB_LAUNCH_CHECK();
     g_launch_count += 2;
+    if (q.split_mode == 1) return launch_splitk_reduce(q, stream);
     return 0;
 }
 
-// error flag of the tensor-core path (0 = fine, 3 = a pipeline wait timed out); checked by tests and the engines' self-test
-int tc_gemm_error() {
-    if (!g_tc_err) return 0;
-    int h = 0;
-    cudaMemcpy(&h, g_tc_err, 4, cudaMemcpyDeviceToHost);
-    return h;
-}
-
-void tc_unregister_weight(const float* w) {
-    auto it = g_w_lo.find(w);
-    if (it == g_w_lo.end()) return;
+void GemmCtx::unregister_weight(const float* w) {
+    auto it = mirrors.find(w);
+    if (it == mirrors.end()) return;
     cudaFree(const_cast<float*>(it->second.hi));      // hi and lo share one allocation
-    g_w_lo.erase(it);
+    mirrors.erase(it);
 }
 
-// lo mirror of a weight matrix (called once per weight at load; the owner unregisters it before freeing the weight)
-int tc_register_weight(const float* w, long long numel) {
-    tc_unregister_weight(w);      // a recycled device address must never inherit a stale mirror
+// tf32 hi / lo mirror of a weight matrix (called once per weight at load; the owner unregisters it before freeing the weight)
+int GemmCtx::register_weight(const float* w, long long numel) {
+    unregister_weight(w);      // a recycled device address must never inherit a stale mirror
     float* buf = nullptr;
     const long long n4 = (numel + 3) / 4;
     MB_CUDA_CHECK(cudaMalloc(&buf, (size_t)n4 * 32));
     tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256>>>(w, buf, buf + n4 * 4, n4);
     MB_LAUNCH_CHECK();
-    g_w_lo[w] = Tf32Mirror{buf, buf + n4 * 4};
+    mirrors[w] = Tf32Mirror{buf, buf + n4 * 4};
     return 0;
 }
 

@@ -1,5 +1,6 @@
 // Internal kernel-launch API of the engine (C++ side; the public C ABI is include/mapperatorinator_b200.h).
 #pragma once
+#include <unordered_map>
 #include "common.cuh"
 
 namespace mb200 {
@@ -18,21 +19,44 @@ struct GemmParams {
     int gate_rpb;
     RowMap R;               // residual (ptr == null -> none)
     int M, N, K;
-    // split-K (set by launch_gemm for small M): CTA z accumulates k in [z*k_per_split, ...) into ws[z][M][N]; a second kernel
-    // reduces the partials in fixed order and applies the epilogue
-    float* splitk_ws; int splitk; int k_per_split;
+    // Split-K.  `splitk` = S is part of the ARITHMETIC of a (N, K) problem — it is chosen from N and K only, never from M or the grid
+    // fill, so a row's result does not depend on how many other rows share the launch (one encoder window alone == the same
+    // window inside a 16-window chunk, bit for bit).  k-range z = [z*k_per_split, (z+1)*k_per_split) is summed on its own and the
+    // S partial sums are added in index order.  HOW the partials are realised is a launch decision that does not change a bit:
+    //   split_mode 1 ("grid"):    CTA z = blockIdx.z writes raw partials to ws[z][M][N]; gemm_splitk_reduce_kernel adds them in order
+    //                             and applies the epilogue (under-filled grids);
+    //   split_mode 2 ("in-tile"): one CTA walks all of K with S accumulators (tcgen05 path: S x 128 TMEM columns) and its epilogue
+    //                             adds them in the same order (large M).
+    float* splitk_ws; int splitk; int k_per_split; int split_mode;
+    long long m_base;       // logical row of local row 0 (launch_gemm slices M when the partial planes of a grid split exceed the workspace)
 };
-int launch_gemm(const GemmParams& p, cudaStream_t stream);
+
+// Per-engine GEMM scratch.  Nothing in here is shared between engines, devices or streams (round-1 had process globals: two
+// engines on two streams raced on them, and a reallocation could pull memory from under a captured CUDA graph).
+struct Tf32Mirror { const float* hi; const float* lo; };
+struct GemmCtx {
+    int num_sms = 148;
+    float* splitk_ws = nullptr; size_t splitk_bytes = 0;        // [S][M][N] partial sums of the grid split
+    float* a_split = nullptr; size_t a_split_bytes = 0;         // tf32 hi | lo copies of the activation operand (tcgen05 path)
+    int* tc_err = nullptr;                                      // device flag: 0 fine, 3 = a pipeline wait timed out
+    bool frozen = false;                                        // set once a CUDA graph holds these pointers: reserve() may no longer move them
+    std::unordered_map<const float*, Tf32Mirror> mirrors;       // weight matrix -> its tf32 hi / lo arrays (filled at finalize)
+    int reserve(size_t splitk_need, size_t a_split_need);       // grow-only; fails loudly when frozen and too small
+    int register_weight(const float* w, long long numel);
+    void unregister_weight(const float* w);
+    int error();                                                // reads tc_err
+    void destroy();
+};
+GemmCtx* default_gemm_ctx();                                    // scratch of the kernel-level test entry points (mb200_op_gemm*)
+int launch_gemm(const GemmParams& p, cudaStream_t stream, GemmCtx* ctx);
 // gemm_tc.cu — tcgen05 3xTF32 path (fp32-grade accuracy on the tensor cores); launch_gemm dispatches to it for large problems
 // whose weight matrix has a registered tf32 "lo" mirror
 extern int g_tc_enabled;
-float* splitk_workspace(size_t need);                       // gemm.cu: shared fixed-size split-K workspace (null if it does not fit)
 int launch_splitk_reduce(const GemmParams& q, cudaStream_t stream);
-bool tc_gemm_eligible(const GemmParams& p);
-int launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
-int tc_register_weight(const float* w, long long numel);
-void tc_unregister_weight(const float* w);
-int tc_gemm_error();
+bool tc_gemm_eligible(const GemmParams& p, GemmCtx* ctx);
+int launch_gemm_tc(const GemmParams& p, cudaStream_t stream, GemmCtx* ctx);
+int gemm_splits_tc(int N, int K, int num_sms, int* k_per_split);      // S of the tensor-core path for an (N, K) problem
+int gemm_splits_simt(int N, int K, int num_sms, int* k_per_split);    // S of the fp32 SIMT path
 
 // ---- norm.cu ---------------------------------------------------------------------------------------------------------
 // y[m, :] = LN(x[m, :]) * w + b                       (affine; w/b may be null)

@@ -143,7 +143,13 @@ class ModelEngine:
         p.min_new_tokens = int(gk.get("min_new_tokens") or 0)
         pad = gk.get("pad_token_id", layout.pad_id)
         p.pad_token_id = int(layout.pad_id if pad is None else pad)
-        p.seed = int(gk.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
+        # The reference draws from torch's global RNG (HF _sample -> torch.multinomial), i.e. a fresh stream per call that
+        # `torch.manual_seed` controls.  Same contract here: without an explicit `seed` every call takes a new 62-bit seed from
+        # torch's default generator (an explicit seed pins the device RNG for tests).
+        seed = gk.get("seed")
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p.do_sample else 0
+        p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         p.time_shift_start, p.time_shift_end = layout.time_shift_start, layout.time_shift_end
         p.position_rule = {"arange": 0, "mask_cumsum": 1}[position_rule]
         if int(gk.get("num_beams", 1) or 1) != 1:

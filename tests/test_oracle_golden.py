@@ -104,3 +104,23 @@ def test_dit_chunked_pipeline_loop():
     pos = dit_oracle.sample_sequence(sd, dc, seq_x, seq_c, y, y_null, 1.0, chunk_noise=cases.dit_chunk_noise, **geo).numpy()
     assert pos.shape == gold["chunked_positions"].shape
     assert np.abs(pos - gold["chunked_positions"]).max() <= 2e-3          # pixels (coordinates are scaled by 512 / 384)
+
+
+@pytest.mark.parametrize("case", ["b1_first_window", "b1_eos_stop"])
+def test_teacher_forced_check_agrees_with_generation(layout, case):
+    """`teacher_forced_check` (one batched decoder pass + processor replay; what bench.py uses to check a WHOLE song against
+    the oracle) must accept the oracle's own greedy output and must flag a corrupted token with its position."""
+    cfg = tiny_model_config(mel=cases.MODEL_FLAVOURS["torchaudio"])
+    sd = init_model_state_dict(cfg, 0)
+    prompt, neg, gk, seed = cases.generate_cases()[case]
+    pcm = cases.model_pcm(cfg, 1, seed)
+    mk = dict(inputs=pcm, decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0))
+    ids, _ = gen_oracle.model_generate(sd, cfg, layout, mk, dict(gk))
+    P = prompt.shape[1]
+    rep = gen_oracle.teacher_forced_check(sd, cfg, layout, pcm, ids, P, dict(gk))
+    assert rep["match"] and rep["n_checked"] == ids.shape[1] - P and rep["min_gap"] > 0
+    bad = ids.clone()
+    k = P + (ids.shape[1] - P) // 2
+    bad[0, k] = (bad[0, k] + 1) % cfg.vocab_size_out
+    rep = gen_oracle.teacher_forced_check(sd, cfg, layout, pcm, bad, P, dict(gk))
+    assert not rep["match"] and rep["first_divergence"]["index"] == k and rep["first_divergence"]["gap"] > 0
