@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define MB200_ABI_VERSION 1
+#define MB200_ABI_VERSION 2
 
 int mb200_abi_version(void);
 const char* mb200_last_error(void);
@@ -88,6 +88,8 @@ typedef struct {
     int32_t n_cond;               /* registered conditional temperatures in processor order */
     float cond_temp[3]; int32_t cond_offset[3]; int32_t cond_flag[3];   /* flag: 16 beat, 32 mania, 64 scroll-speed */
     int32_t position_rule;        /* 0 = arange (transformers 5.x), 1 = mask cumsum (4.5x) */
+    float top_p_cut;              /* (float)(1.0 - top_p) evaluated in DOUBLE like HF's `cumulative_probs <= (1 - self.top_p)` with a Python
+                                     float top_p (logits_process.py TopPLogitsWarper): 1.0f - (float)0.95 is one ulp away from it */
 } mb200_generate_params;
 
 /* GenerationMixin.generate as called by server.model_generate (server.py:143-150): prefill + token loop with the fused
@@ -155,6 +157,13 @@ int mb200_dit_sample_loop(mb200_dit* d, const float* z, const float* c, const fl
 int64_t mb200_launch_count(void);
 /* option "pdl": 1 = capture the token-step graph with programmatic dependent launch edges. */
 int mb200_model_set_option(mb200_model* m, const char* name, int32_t value);
+/* Parity hook for the fused logits-processor chain (server.py:106-134 + HF min-new-tokens / top-k / top-p + selection): ONE selection
+ * step on caller-supplied logits.  logits DEVICE [rows, V] (rows = 2B under CFG, negative-prompt rows first); ids HOST [B, L];
+ * `step` / `has_last_scores` select the look-back-bias state left by the previous call.  scores_out DEVICE [B, V] = the scores the
+ * selection sees (-inf = removed), chosen_out HOST [B]. */
+int mb200_model_logits_chain(mb200_model* m, const float* logits, int32_t B, int32_t use_cfg, const int64_t* ids, int32_t L, int32_t prompt_len,
+                             const uint8_t* vflags, const mb200_generate_params* gp, int32_t step, int32_t has_last_scores, float* scores_out,
+                             int64_t* chosen_out, void* cuda_stream);
 /* option "graph": 1 (default) = every step of mb200_dit_sample_loop is one replay of a captured CUDA graph, 0 = eager launches. */
 int mb200_dit_set_option(mb200_dit* d, const char* name, int32_t value);
 /* Re-runs the token step eagerly `iters` times on the state of the last generate() call with CUDA events around every

@@ -32,7 +32,7 @@ class GenerateParamsC(C.Structure):
                 ("max_length", C.c_int32), ("min_new_tokens", C.c_int32), ("pad_token_id", C.c_int32), ("seed", C.c_uint64),
                 ("time_shift_start", C.c_int32), ("time_shift_end", C.c_int32), ("n_cond", C.c_int32),
                 ("cond_temp", C.c_float * 3), ("cond_offset", C.c_int32 * 3), ("cond_flag", C.c_int32 * 3),
-                ("position_rule", C.c_int32)]
+                ("position_rule", C.c_int32), ("top_p_cut", C.c_float)]
 
 
 class DitConfigC(C.Structure):
@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "mb200_model_generate", "mb200_model_forward_logits",
     "mb200_dit_create", "mb200_dit_destroy", "mb200_dit_set_weight", "mb200_dit_finalize", "mb200_dit_forward_with_cfg",
     "mb200_dit_sample_loop", "mb200_dit_set_option",
-    "mb200_launch_count", "mb200_model_set_option", "mb200_model_profile_step", "mb200_model_read_trace", "mb200_model_mega_stats",
+    "mb200_launch_count", "mb200_model_set_option", "mb200_model_profile_step", "mb200_model_read_trace", "mb200_model_mega_stats", "mb200_model_logits_chain",
     "mb200_op_gemm", "mb200_op_gemm_tc", "mb200_set_tensor_cores", "mb200_op_layernorm", "mb200_op_attention",
 ]
 
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
     lib.mb200_dit_finalize.argtypes = [vp]
     lib.mb200_dit_forward_with_cfg.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, C.POINTER(DitMaskC), vp, vp]
     lib.mb200_dit_sample_loop.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, C.POINTER(DitMaskC), vp, i32, vp, vp, vp]
+    lib.mb200_model_logits_chain.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, C.POINTER(GenerateParamsC), i32, i32, vp, vp, vp]
     lib.mb200_dit_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.mb200_op_gemm.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, f32, vp, i64, vp, i64, i32, i32, i32, i32, vp]
     lib.mb200_op_gemm_tc.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, f32, vp, i64, i32, i32, i32, vp]

@@ -680,6 +680,7 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
     // (6)-(7) selection
     int chosen = 0;
     if (!c.do_sample) {
+        if (p.dbg_scores) { _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) p.dbg_scores[(long long)b * V + v] = s[v]; }
         // argmax, first index on ties (torch.argmax)
         float best = -INFINITY; int bi = 0x7fffffff;
         _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
@@ -733,39 +734,80 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
                 __syncthreads();
             }
         }
-        // softmax over the (possibly sorted) entries
+        // softmax statistics over the (possibly sorted) entries
         float m = -INFINITY;
         _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) m = fmaxf(m, s[v]);
         m = block_reduce(m, true, scratch);
-        float z = 0.f;
-        _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) z += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m);
-        z = block_reduce(z, false, scratch);
-        // serial inclusive scan by one warp-strided pass is overkill for V<=4096: thread 0 walks (V adds) — negligible vs
-        // a decoder step, and gives a fixed summation order.
-        if (tid == 0) {
-            float keep_from = 0;   // index of first kept entry for top-p
-            int first_keep = 0;
-            if (need_sort && c.top_p < 1.0f) {
-                float cum = 0.f;
-                const float cut = 1.0f - c.top_p;
-                for (int v = 0; v < V - 1; ++v) {     // the last (largest) entry is always kept (min_tokens_to_keep = 1)
-                    cum += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m) / z;
-                    if (cum <= cut) first_keep = v + 1; else break;
-                }
-            }
-            (void)keep_from;
-            float zk = 0.f;
-            for (int v = first_keep; v < V; ++v) zk += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m);
-            unsigned long long r = splitmix64(c.seed ^ splitmix64(((unsigned long long)st_step << 20) ^ (unsigned long long)b));
-            float u = (float)((r >> 40) + 0.5) * (1.0f / 16777216.0f) * zk;
-            float cum = 0.f;
-            int pick = V - 1;
-            for (int v = first_keep; v < V; ++v) {
-                cum += (s[v] == -INFINITY) ? 0.f : expf(s[v] - m);
-                if (cum >= u) { pick = v; break; }
-            }
-            sm.chosen_sh = sidx[pick];
+        // Inclusive prefix sums of e[v] = exp(s[v] - m) in array order (ascending scores when sorted) by a block scan: thread t owns
+        // the contiguous segment [t*SEG, (t+1)*SEG) (sequential inside, like the serial walk it replaces), warp shuffles scan the
+        // segment totals, one warp scans the 16 warp totals.  The three serial thread-0 passes over V with expf (round 1) are gone.
+        constexpr int SEG = VMAX / SAMPLE_THREADS;
+        const int lane = tid & 31, warp = tid >> 5;
+        float loc[SEG];
+        float run = 0.f;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+            const int v = tid * SEG + j;
+            const float e = (v < V && s[v] != -INFINITY) ? expf(s[v] - m) : 0.f;
+            run += e;
+            loc[j] = run;
         }
+        float incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) scratch[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            float w = lane < SAMPLE_THREADS / 32 ? scratch[lane] : 0.f;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            scratch[lane] = w;                               // inclusive scan of the warp totals; scratch[15] = z
+        }
+        __syncthreads();
+        const float base = (incl - run) + (warp > 0 ? scratch[warp - 1] : 0.f);
+        const float z = scratch[SAMPLE_THREADS / 32 - 1];
+        __syncthreads();
+        // top-p (HF TopPLogitsWarper, min_tokens_to_keep = 1): in ascending order remove the longest prefix whose cumulative probability
+        // is <= 1 - top_p; the last (largest) entry always stays.  The prefix sums are monotone, so its length is a count.
+        int first_keep = 0;
+        if (need_sort && c.top_p < 1.0f) {
+            const float cut = c.top_p_cut;
+            float cnt = 0.f;
+#pragma unroll
+            for (int j = 0; j < SEG; ++j) {
+                const int v = tid * SEG + j;
+                if (v < V - 1 && (base + loc[j]) / z <= cut) cnt += 1.f;
+            }
+            first_keep = (int)block_reduce(cnt, false, scratch);
+        }
+        if (p.dbg_scores) {       // parity hook (tests): the scores the selection sees, -inf = removed by top-k / top-p, original id order
+            _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) p.dbg_scores[(long long)b * V + sidx[v]] = v < first_keep ? -INFINITY : s[v];
+        }
+        // mass below the kept set, then inverse-CDF draw over the kept entries
+        if (tid == 0) scratch[33] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SEG; ++j)
+            if (tid * SEG + j == first_keep - 1) scratch[33] = base + loc[j];
+        __syncthreads();
+        const float below = scratch[33];
+        const unsigned long long r = splitmix64(c.seed ^ splitmix64(((unsigned long long)st_step << 20) ^ (unsigned long long)b));
+        const float u = below + (float)((r >> 40) + 0.5) * (1.0f / 16777216.0f) * (z - below);
+        float cnt = 0.f;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+            const int v = tid * SEG + j;
+            if (v >= first_keep && v < V && base + loc[j] < u) cnt += 1.f;
+        }
+        const int pick = min(V - 1, first_keep + (int)block_reduce(cnt, false, scratch));
+        if (tid == 0) sm.chosen_sh = sidx[pick];
         __syncthreads();
         chosen = sm.chosen_sh;
     }

@@ -695,6 +695,18 @@ static bool mega_eligible(const mb200_model* m, int rows) {
            fits(c.d_model, c.ffn_dim) && fits(c.vocab_size_out, c.d_model);
 }
 
+static SampleConfig make_sample_config(const mb200_generate_params* gp, int B, bool use_cfg, int V, int ids_ld) {
+    SampleConfig sc{};
+    sc.B = B; sc.use_cfg = use_cfg ? 1 : 0; sc.cfg_scale = gp->cfg_scale; sc.V = V; sc.ts_start = gp->time_shift_start; sc.ts_end = gp->time_shift_end;
+    sc.timeshift_bias = gp->timeshift_bias; sc.types_first = gp->types_first; sc.temperature = gp->temperature;
+    sc.n_cond = gp->n_cond;
+    for (int i = 0; i < 3; ++i) { sc.cond_temp[i] = gp->cond_temp[i]; sc.cond_offset[i] = gp->cond_offset[i]; sc.cond_flag[i] = gp->cond_flag[i]; }
+    sc.lookback_on = gp->lookback_on; sc.lookback_start = gp->lookback_start; sc.lookback_end = gp->lookback_end;
+    sc.do_sample = gp->do_sample; sc.top_k = gp->top_k; sc.top_p = gp->top_p; sc.top_p_cut = gp->top_p_cut; sc.seed = gp->seed; sc.pad_id = gp->pad_token_id;
+    sc.pos_rule_cumsum = gp->position_rule; sc.ids_ld = ids_ld;
+    return sc;
+}
+
 // =====================================================================================================================
 extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_t B, const int64_t* prompt, const uint8_t* prompt_mask,
                                     int32_t P, const int64_t* neg_prompt, const uint8_t* neg_mask, const uint8_t* vflags,
@@ -736,14 +748,7 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
         for (int t = 0; t < P; ++t) idsrow[(size_t)b * ids_ld + t] = prompt[(size_t)b * P + t];
     GenState gs{};
     gs.cur_len = P; gs.prompt_len = P; gs.max_length = gp->max_length; gs.min_new_tokens = gp->min_new_tokens;
-    SampleConfig sc{};
-    sc.B = B; sc.use_cfg = use_cfg ? 1 : 0; sc.cfg_scale = gp->cfg_scale; sc.V = V; sc.ts_start = gp->time_shift_start; sc.ts_end = gp->time_shift_end;
-    sc.timeshift_bias = gp->timeshift_bias; sc.types_first = gp->types_first; sc.temperature = gp->temperature;
-    sc.n_cond = gp->n_cond;
-    for (int i = 0; i < 3; ++i) { sc.cond_temp[i] = gp->cond_temp[i]; sc.cond_offset[i] = gp->cond_offset[i]; sc.cond_flag[i] = gp->cond_flag[i]; }
-    sc.lookback_on = gp->lookback_on; sc.lookback_start = gp->lookback_start; sc.lookback_end = gp->lookback_end;
-    sc.do_sample = gp->do_sample; sc.top_k = gp->top_k; sc.top_p = gp->top_p; sc.seed = gp->seed; sc.pad_id = gp->pad_token_id;
-    sc.pos_rule_cumsum = gp->position_rule; sc.ids_ld = ids_ld;
+    const SampleConfig sc = make_sample_config(gp, B, use_cfg, V, ids_ld);
 
     MB_CUDA_CHECK(cudaMemcpyAsync(m->g_prefill_ids.p, pre.data(), pre.size() * 8, cudaMemcpyHostToDevice, st));
     MB_CUDA_CHECK(cudaMemcpyAsync(m->g_ids.p, idsrow.data(), idsrow.size() * 8, cudaMemcpyHostToDevice, st));
@@ -964,5 +969,45 @@ extern "C" int mb200_model_mega_stats(mb200_model* m, double* out, int32_t reset
     MB_REQUIRE(m && out, "null argument");
     out[0] = (double)m->mega_launches; out[1] = m->mega_ms; out[2] = (double)m->mega_tokens;
     if (reset) { m->mega_launches = 0; m->mega_ms = 0.0; m->mega_tokens = 0; }
+    return 0;
+}
+
+// Parity hook for the fused logits-processor chain (tests; not part of the reference-facing boundary): runs ONE selection step of
+// `sample_body` on caller-supplied logits.  logits: DEVICE [rows, V] (rows = 2B under CFG, negative-prompt rows first);
+// ids: HOST [B, L] the tokens so far (prompt + generated); `step` / `has_last_scores` select the look-back-bias state left by the
+// previous call (scores are double-buffered by step parity, exactly as in generation).  Outputs: scores_out DEVICE [B, V] = the scores
+// the selection sees (-inf where MinNewTokens / MonotonicTimeShift / LookbackBias / top-k / top-p removed the id), chosen_out HOST [B].
+extern "C" int mb200_model_logits_chain(mb200_model* m, const float* logits, int32_t B, int32_t use_cfg, const int64_t* ids, int32_t L,
+                                        int32_t prompt_len, const uint8_t* vflags, const mb200_generate_params* gp, int32_t step,
+                                        int32_t has_last_scores, float* scores_out, int64_t* chosen_out, void* stream) {
+    MB_REQUIRE(m && m->finalized && logits && ids && vflags && gp && scores_out && chosen_out, "null argument");
+    const auto& c = m->cfg;
+    const int rows = use_cfg ? 2 * B : B, V = c.vocab_size_out, ids_ld = c.tgt_seq_len;
+    MB_REQUIRE(B >= 1 && rows <= m->max_rows && L >= 1 && L < ids_ld, "bad batch / length");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<long long> idsrow((size_t)B * ids_ld, (long long)gp->pad_token_id);
+    for (int b = 0; b < B; ++b)
+        for (int t = 0; t < L; ++t) idsrow[(size_t)b * ids_ld + t] = ids[(size_t)b * L + t];
+    GenState gs{};
+    gs.cur_len = L; gs.prompt_len = prompt_len; gs.max_length = gp->max_length; gs.min_new_tokens = gp->min_new_tokens;
+    gs.step = step; gs.has_last_scores = has_last_scores;
+    const SampleConfig sc = make_sample_config(gp, B, use_cfg != 0, V, ids_ld);
+    std::vector<int> zeros(rows, 0);
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->g_ids.p, idsrow.data(), idsrow.size() * 8, cudaMemcpyHostToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->g_vflags.p, vflags, c.vocab_size_in, cudaMemcpyHostToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->g_state.p, &gs, sizeof(gs), cudaMemcpyHostToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->g_cfg.p, &sc, sizeof(sc), cudaMemcpyHostToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->g_leftpad.p, zeros.data(), rows * 4, cudaMemcpyHostToDevice, st));
+    MB_CUDA_CHECK(cudaMemsetAsync(m->g_finished.p, 0, m->max_rows, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->d_logits.p, logits, (size_t)rows * V * 4, cudaMemcpyDeviceToDevice, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    MB_TRY(launch_prompt_scan(m->g_ids.as<long long>(), ids_ld, B, L, m->g_vflags.as<unsigned char>(), sc.ts_start, sc.ts_end, m->g_lastts.as<int>(), st));
+    SampleParams sp = sample_params(m, rows);
+    sp.dbg_scores = scores_out;
+    MB_TRY(launch_sample(sp, B, st, false));
+    std::vector<long long> chosen(B);
+    MB_CUDA_CHECK(cudaMemcpy2DAsync(chosen.data(), 8, m->g_ids.as<long long>() + L, (size_t)ids_ld * 8, 8, B, cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; ++b) chosen_out[b] = chosen[b];
     return 0;
 }

@@ -136,7 +136,7 @@ struct SampleConfig {        // device-resident, rewritten by the host once per 
     int n_cond;              // conditional temperatures (logit_processors.py:62-71), evaluated on batch row 0 only
     float cond_temp[3]; int cond_offset[3]; int cond_flag[3];   // flag = VF_BEAT / VF_MANIA / VF_SCROLL
     int lookback_on; int lookback_start, lookback_end;           // LookbackBiasLogitsWarper range
-    int do_sample; int top_k; float top_p;
+    int do_sample; int top_k; float top_p; float top_p_cut;      // top_p_cut = (float)(1.0 - (double)top_p), see mb200_generate_params
     unsigned long long seed;
     int pad_id;
     int pos_rule_cumsum;     // 0: position = index (transformers 5.x), 1: index - n_left_pad[b] (4.5x)
@@ -195,6 +195,7 @@ struct SampleParams {
     const float* tok_emb; const float* pos_emb; int d_model;   // decoder_embedder / embed_positions
     float* x_out; long long x_ld;                   // [rows, d_model] residual stream input of the next step
     int rows;
+    float* dbg_scores;                              // parity hook, null in production: [B, V] scores the selection sees (-inf = removed)
 };
 int launch_sample(const SampleParams& p, int B, cudaStream_t stream, bool pdl);
 

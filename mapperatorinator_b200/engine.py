@@ -101,13 +101,9 @@ class ModelEngine:
         return out
 
     # ---- decoder ---------------------------------------------------------------------------------------------------
-    def generate(self, slots: Sequence[int], prompt: torch.Tensor, prompt_mask: Optional[torch.Tensor], layout: TokenLayout,
-                 generate_kwargs: dict, negative_prompt: Optional[torch.Tensor] = None,
-                 negative_mask: Optional[torch.Tensor] = None, position_rule: str = "arange") -> torch.Tensor:
-        """The token loop of `server.model_generate` for rows whose encoder states already sit in `slots`.
-        Returns a CPU LongTensor (B, L) = prompt + generated, like the reference."""
+    def _generate_params(self, layout: TokenLayout, generate_kwargs: dict, position_rule: str = "arange"):
+        """generate_kwargs (server.py:83-134 names) -> the C struct + the EOS id set."""
         gk = dict(generate_kwargs)
-        B, P = prompt.shape
         t = float(gk.get("temperature", 1.0))
         types_first = bool(gk.get("types_first", False))
         lookback_time = float(gk.get("lookback_time", 0.0))
@@ -139,6 +135,7 @@ class ModelEngine:
         p.do_sample = int(bool(gk.get("do_sample", False)))
         p.top_k = int(gk.get("top_k", 0) or 0)
         p.top_p = float(gk.get("top_p", 1.0) if gk.get("top_p") is not None else 1.0)
+        p.top_p_cut = 1.0 - float(gk.get("top_p", 1.0) if gk.get("top_p") is not None else 1.0)      # double arithmetic, then one rounding to f32
         p.max_length = int(gk.get("max_length", self.cfg.tgt_seq_len))
         p.min_new_tokens = int(gk.get("min_new_tokens") or 0)
         pad = gk.get("pad_token_id", layout.pad_id)
@@ -152,6 +149,15 @@ class ModelEngine:
         p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         p.time_shift_start, p.time_shift_end = layout.time_shift_start, layout.time_shift_end
         p.position_rule = {"arange": 0, "mask_cumsum": 1}[position_rule]
+        return p, eos_ids, gk
+
+    def generate(self, slots: Sequence[int], prompt: torch.Tensor, prompt_mask: Optional[torch.Tensor], layout: TokenLayout,
+                 generate_kwargs: dict, negative_prompt: Optional[torch.Tensor] = None,
+                 negative_mask: Optional[torch.Tensor] = None, position_rule: str = "arange") -> torch.Tensor:
+        """The token loop of `server.model_generate` for rows whose encoder states already sit in `slots`.
+        Returns a CPU LongTensor (B, L) = prompt + generated, like the reference."""
+        p, eos_ids, gk = self._generate_params(layout, generate_kwargs, position_rule)
+        B, P = prompt.shape
         if int(gk.get("num_beams", 1) or 1) != 1:
             raise NotImplementedError("beam search is outside the hot path (SURVEY §8: greedy / sampling only)")
         use_cfg = negative_prompt is not None and p.cfg_scale > 1.0
@@ -179,6 +185,23 @@ class ModelEngine:
                 C.byref(p), out.ctypes.data, C.byref(out_len), _stream()))
         L = out_len.value
         return torch.from_numpy(out.reshape(-1)[: B * L].reshape(B, L).copy())
+
+    def logits_chain(self, logits: torch.Tensor, ids: torch.Tensor, prompt_len: int, layout: TokenLayout, generate_kwargs: dict,
+                     step: int = 0, has_last_scores: bool = False, use_cfg: bool = False):
+        """Parity hook: one selection step of the fused logits-processor chain on given logits (rows, V) CUDA f32 and ids (B, L).
+        Returns (scores (B, V) CUDA — what the selection sees, -inf = removed —, chosen (B,) CPU)."""
+        p, eos_ids, gk = self._generate_params(layout, generate_kwargs)
+        B, L = ids.shape
+        a = np.ascontiguousarray(ids.detach().cpu().numpy().astype(np.int64))
+        vflags = build_vflags(layout, eos_ids)
+        logits = logits.contiguous().float()
+        scores = torch.empty(B, self.cfg.vocab_size_out, device=logits.device, dtype=torch.float32)
+        chosen = np.zeros(B, dtype=np.int64)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mb200_model_logits_chain(self.handle, logits.data_ptr(), B, int(use_cfg), a.ctypes.data, L, int(prompt_len),
+                                                         vflags.ctypes.data, C.byref(p), int(step), int(has_last_scores), scores.data_ptr(),
+                                                         chosen.ctypes.data, _stream()))
+        return scores, torch.from_numpy(chosen)
 
     def forward_logits(self, slots: Sequence[int], ids: torch.Tensor, mask: Optional[torch.Tensor],
                        position_rule: str = "arange") -> torch.Tensor:

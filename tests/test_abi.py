@@ -20,7 +20,7 @@ def test_header_and_binding_agree():
 def test_library_exports_every_symbol():
     assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
     lib = _lib.load()
-    assert lib.mb200_abi_version() == 1
+    assert lib.mb200_abi_version() == 2
     for sym in _header_symbols():
         assert hasattr(lib, sym), sym
 

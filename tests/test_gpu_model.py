@@ -122,6 +122,85 @@ def test_sampling_is_valid_and_seeded(tiny, layout):
     assert int(a[:, 4:].max()) < cfg.vocab_size_out and a.shape == (1, 36)
 
 
+def _chain_case(layout, cfg, B, seed):
+    """Two consecutive selection steps on synthetic logits: ids0 (prompt with a time shift after SOS -> MonotonicTimeShift active),
+    then ids1 = ids0 + one token per row (row 0: a TIMED type token -> the LookbackBias branch fires; row 1: a plain time shift)."""
+    g = torch.Generator().manual_seed(seed)
+    V = cfg.vocab_size_out
+    ts0 = layout.time_shift_start
+    timed = sorted(layout.timed_token_ids())[3]
+    rows = [[3700, 3705, 1, 9, timed, ts0 + 40, 3601], [3701, 3706, 1, 9, timed, ts0 + 12, 3602], [3702, 3707, 1, 9, timed, ts0 + 300, 3603]][:B]
+    ids0 = torch.tensor(rows)
+    nxt = torch.tensor([[timed], [ts0 + 44], [timed]][:B])
+    ids1 = torch.cat([ids0, nxt], 1)
+    return ids0, ids1, torch.randn(B, V, generator=g) * 2.5, torch.randn(B, V, generator=g) * 2.5
+
+
+@pytest.mark.parametrize("top_k,top_p", [(0, 0.95), (50, 0.95), (50, 1.0), (0, 0.9), (0, 1.0)])
+@pytest.mark.parametrize("B", [1, 3])
+def test_sampling_chain_keep_set_matches_oracle(tiny, layout, top_k, top_p, B):
+    """The reference's production mode (configs/inference/default.yaml:45-56: do_sample, top_p 0.95) through the fused chain vs
+    `oracle.generate.Processors` (pinned branch by branch to the reference processors + HF warpers): the set of ids that survive
+    MinNewTokens / MonotonicTimeShift / LookbackBias / TopK / TopP must be IDENTICAL, the renormalised probabilities equal to 1e-6,
+    and the drawn token must lie in the keep-set.  Two consecutive steps, so LookbackBias runs with real `last_scores`."""
+    from oracle import generate as go
+    _, cfg, sd, model = tiny
+    ids0, ids1, l0, l1 = _chain_case(layout, cfg, B, 100 * top_k + B)
+    P = 4
+    gk = dict(cases.GK, do_sample=True, top_p=top_p, top_k=top_k, max_length=64, min_new_tokens=8, lookback_time=4092.0, lookahead_time=3273.6,
+              context_type="map", seed=1234)
+    pr = go.Processors(layout, B, P, gk)
+    for step, (ids, lg) in enumerate(((ids0, l0), (ids1, l1))):
+        want = pr(ids, lg)
+        got, chosen = model.engine.logits_chain(lg.cuda(), ids, P, layout, gk, step=step, has_last_scores=step > 0)
+        got = got.cpu()
+        keep_w, keep_g = want != float("-inf"), got != float("-inf")
+        assert torch.equal(keep_w, keep_g), f"step {step}: keep-sets differ at {(keep_w != keep_g).nonzero()[:5].tolist()} (|want|={int(keep_w.sum())}, |got|={int(keep_g.sum())})"
+        pw, pg = torch.softmax(want, -1), torch.softmax(got, -1)
+        assert (pw - pg).abs().max() <= 1e-6, (pw - pg).abs().max()
+        for b in range(B):
+            assert keep_w[b, int(chosen[b])], f"step {step} row {b}: drew id {int(chosen[b])} outside the keep-set"
+    if top_p < 1.0:
+        assert int(keep_w.sum()) < B * cfg.vocab_size_out            # the warpers did remove something
+
+
+def test_sampler_follows_the_processed_distribution(tiny, layout):
+    """Chi-square test of the device sampler (inverse CDF over the kept entries, splitmix64 counter RNG): 3 000 independent seeds on one
+    fixed distribution (top_k = 6) against the oracle's probabilities.  5 degrees of freedom: chi2 < 25.7 at p = 1e-4."""
+    from oracle import generate as go
+    _, cfg, sd, model = tiny
+    ids0, _, l0, _ = _chain_case(layout, cfg, 1, 9)
+    gk = dict(cases.GK, do_sample=True, top_p=1.0, top_k=6, max_length=64, lookback_time=0.0, lookahead_time=0.0, context_type="map")
+    want = go.Processors(layout, 1, 4, gk)(ids0, l0)
+    probs = torch.softmax(want, -1)[0]
+    support = (probs > 0).nonzero().flatten().tolist()
+    assert len(support) == 6
+    counts = {i: 0 for i in support}
+    n = 3000
+    lg = l0.cuda()
+    for seed in range(n):
+        _, chosen = model.engine.logits_chain(lg, ids0, 4, layout, dict(gk, seed=seed), step=0)
+        counts[int(chosen[0])] += 1                                   # KeyError = a draw outside the support
+    chi2 = sum((counts[i] - n * float(probs[i])) ** 2 / (n * float(probs[i])) for i in support)
+    assert chi2 < 25.7, (chi2, counts, [float(probs[i]) for i in support])
+
+
+def test_sampling_uses_a_fresh_seed_per_call(tiny, layout):
+    """Without an explicit `seed` the engine draws one per call from torch's default generator (the reference samples from torch's
+    global RNG): two calls differ, `torch.manual_seed` reproduces them."""
+    from mapperatorinator_b200.server import model_generate
+    _, cfg, sd, model = tiny
+    prompt = torch.tensor([[3700, 3705, 1, 9]])
+    gk = dict(cases.GK, do_sample=True, top_p=0.95, max_length=4 + 32, min_new_tokens=32, lookback_time=0.0, lookahead_time=0.0, context_type="map")
+    mk = dict(inputs=cases.model_pcm(cfg, 1), decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0))
+    torch.manual_seed(99)
+    a, _ = model_generate(model, layout, dict(mk), dict(gk))
+    b, _ = model_generate(model, layout, dict(mk), dict(gk))
+    torch.manual_seed(99)
+    a2, _ = model_generate(model, layout, dict(mk), dict(gk))
+    assert not torch.equal(a, b) and torch.equal(a, a2)
+
+
 def test_song_decoder_equals_per_window_calls(tiny, layout):
     """Resident-encoder sequential loop (pipeline.SongDecoder) == the reference call pattern (one model_generate
     per window, encoder re-run each time)."""
