@@ -12,6 +12,56 @@ __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterp
 __device__ __forceinline__ float2 ldcg2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
 __device__ __forceinline__ int ld_state(const int* p) { return __ldcg(p); }
 
+// ---- tagged pairs of the dataflow megakernel (decode_mega2.cu): one 64-bit word = fp32 bits | tag << 32, written by ONE 64-bit
+// store, so a reader that sees the expected tag also sees the value (NCCL's "LL" protocol).  Scalar 64-bit accesses: single-copy atomic.
+typedef unsigned long long ll_t;
+__device__ __forceinline__ void ll_store(ll_t* p, float v, unsigned tag) {
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(((ll_t)tag << 32) | (ll_t)__float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ void ll_store2(ll_t* p, float a, float b, unsigned tag) {      // p 16-byte aligned
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(((ll_t)tag << 32) | (ll_t)__float_as_uint(a)),
+                 "l"(((ll_t)tag << 32) | (ll_t)__float_as_uint(b)) : "memory");
+}
+__device__ __forceinline__ void ll_load2(const ll_t* p, ll_t& a, ll_t& b) {                // p 16-byte aligned
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+constexpr long long LL_SPIN_LIMIT = 1ll << 24;      // ~ seconds; a dataflow wait that long is a bug, never a slow producer
+// Wait for one / two / four consecutive pairs carrying `tag`.  Bounded: on a timeout (or when another CTA raised `err`) the error flag is
+// set and zeros are returned, so a logic error ends the launch instead of hanging the GPU.
+__device__ __forceinline__ bool ll_spin_check(long long& spin, int* err) {
+    if ((++spin & 0x3FF) == 0 && (spin > LL_SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0)) { atomicCAS(err, 0, 4); return false; }
+    return true;
+}
+__device__ __forceinline__ float ll_wait1(const ll_t* p, unsigned tag, int* err) {
+    ll_t v;
+    long long spin = 0;
+    while (true) {
+        asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if ((unsigned)(v >> 32) == tag) return __uint_as_float((unsigned)v);
+        if (!ll_spin_check(spin, err)) return 0.f;
+    }
+}
+__device__ __forceinline__ float2 ll_wait2(const ll_t* p, unsigned tag, int* err) {
+    ll_t a, b;
+    long long spin = 0;
+    while (true) {
+        ll_load2(p, a, b);
+        if ((unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag) return make_float2(__uint_as_float((unsigned)a), __uint_as_float((unsigned)b));
+        if (!ll_spin_check(spin, err)) return make_float2(0.f, 0.f);
+    }
+}
+__device__ __forceinline__ float4 ll_wait4(const ll_t* p, unsigned tag, int* err) {        // p 32-byte aligned
+    ll_t a, b, c, d;
+    long long spin = 0;
+    while (true) {
+        ll_load2(p, a, b);
+        ll_load2(p + 2, c, d);
+        if ((unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag && (unsigned)(c >> 32) == tag && (unsigned)(d >> 32) == tag)
+            return make_float4(__uint_as_float((unsigned)a), __uint_as_float((unsigned)b), __uint_as_float((unsigned)c), __uint_as_float((unsigned)d));
+        if (!ll_spin_check(spin, err)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // activation staging for the GEMV family: xs[NB][K] <- LayerNorm(x) | x
 // ---------------------------------------------------------------------------------------------------------------------
@@ -119,23 +169,13 @@ __device__ __forceinline__ void gemv_row_operands(const GemvParams& p, int n, in
     }
 }
 
+// dot(W[n, :], xs[b, :]) for NB batch rows; lane b < NB ends up holding row b's sum in `mine`.  Four independent accumulation chains
+// per batch row (the x / y / z / w components of the float4 stream), merged as (x + y) + (z + w) before the shuffle tree.  Shared by
+// every decode driver (per-kernel GEMV, barrier megakernel, dataflow megakernel): same order, same bits.
 template <int NB, bool W_GLOBAL>
-__device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float* wrow_f, const float* xs, int b0, int lane, int cur_pos,
-                                         bool have_operands = false, float bias_v = 0.f, float r_v = 0.f, unsigned long long* dbg = nullptr) {
-    const int K = p.K, K4 = K >> 2;
+__device__ __forceinline__ float gemv_dot(int K, const float* wrow_f, const float* xs, int lane, unsigned long long* dbg = nullptr) {
+    const int K4 = K >> 2;
     const float4* wrow = reinterpret_cast<const float4*>(wrow_f);
-    if (!have_operands) gemv_row_operands<NB>(p, n, b0, lane, bias_v, r_v);
-    // Everything the epilogue needs besides the dot product is derived NOW, branch-free and for every lane (batch index clamped), so
-    // its shared-memory lookups overlap the dot product instead of forming a ~0.25 us dependent chain behind the shuffle tree.
-    const int bl = min(b0 + (lane < NB ? lane : 0), p.B - 1);
-    const int si = (int)(p.nseg > 1 && n >= p.seg[1].n_begin) + (int)(p.nseg > 2 && n >= p.seg[2].n_begin);
-    const GemvSeg& sg = p.seg[si];
-    float* const outp = sg.out + ((long long)bl * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin));
-    const int act = sg.act;
-    const float alpha = sg.alpha;
-    const bool has_bias = p.bias != nullptr, has_res = p.R != nullptr;
-    // four independent accumulation chains per batch row (the x / y / z / w components of the float4 stream) instead of one
-    // 4*K/128-deep dependent FMA chain; merged as (x + y) + (z + w) before the shuffle tree
     float4 acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -169,6 +209,23 @@ __device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float
         if (lane == b) mine = s;
     }
     if (dbg && lane == 0) dbg[1] = (unsigned long long)clock64();
+    return mine;
+}
+
+template <int NB, bool W_GLOBAL>
+__device__ __forceinline__ void gemv_row(const GemvParams& p, int n, const float* wrow_f, const float* xs, int b0, int lane, int cur_pos,
+                                         bool have_operands = false, float bias_v = 0.f, float r_v = 0.f, unsigned long long* dbg = nullptr) {
+    if (!have_operands) gemv_row_operands<NB>(p, n, b0, lane, bias_v, r_v);
+    // Everything the epilogue needs besides the dot product is derived NOW, branch-free and for every lane (batch index clamped), so
+    // its shared-memory lookups overlap the dot product instead of forming a ~0.25 us dependent chain behind the shuffle tree.
+    const int bl = min(b0 + (lane < NB ? lane : 0), p.B - 1);
+    const int si = (int)(p.nseg > 1 && n >= p.seg[1].n_begin) + (int)(p.nseg > 2 && n >= p.seg[2].n_begin);
+    const GemvSeg& sg = p.seg[si];
+    float* const outp = sg.out + ((long long)bl * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin));
+    const int act = sg.act;
+    const float alpha = sg.alpha;
+    const bool has_bias = p.bias != nullptr, has_res = p.R != nullptr;
+    const float mine = gemv_dot<NB, W_GLOBAL>(p.K, wrow_f, xs, lane, dbg);
     if (lane < NB && b0 + lane < p.B) {
         float v = mine;
         if (has_bias) v += bias_v;
@@ -601,11 +658,17 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         float x;
         const bool eos = (p.vflags[v] & VF_EOS) != 0;
         if (c.use_cfg) {
-            float cond = __ldcg(p.logits + (long long)b * p.logits_ld + v);          // first half = "conditional" in HF's processor
-            float unc = __ldcg(p.logits + (long long)(B + b) * p.logits_ld + v);
+            float cond, unc;                                                          // first half = "conditional" in HF's processor
+            if (p.ll_logits) {
+                cond = ll_wait1(p.ll_logits + (long long)b * V + v, p.ll_in_tag, p.ll_err);
+                unc = ll_wait1(p.ll_logits + (long long)(B + b) * V + v, p.ll_in_tag, p.ll_err);
+            } else {
+                cond = __ldcg(p.logits + (long long)b * p.logits_ld + v);
+                unc = __ldcg(p.logits + (long long)(B + b) * p.logits_ld + v);
+            }
             x = (suppress_eos && eos) ? -INFINITY : unc + (cond - unc) * c.cfg_scale;
         } else {
-            x = __ldcg(p.logits + (long long)b * p.logits_ld + v);
+            x = p.ll_logits ? ll_wait1(p.ll_logits + (long long)b * V + v, p.ll_in_tag, p.ll_err) : __ldcg(p.logits + (long long)b * p.logits_ld + v);
             if (suppress_eos && eos) x = -INFINITY;
         }
         s[v] = x;
@@ -836,7 +899,13 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         float4* xo = reinterpret_cast<float4*>(p.x_out + (long long)row * p.x_ld);
         for (int i = tid; i < p.d_model / 4; i += SAMPLE_THREADS) {
             float4 a = te[i], q = pe[i];
-            xo[i] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+            const float4 o = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+            xo[i] = o;
+            if (p.ll_x_out) {
+                ll_t* lo = p.ll_x_out + (long long)row * p.d_model + i * 4;
+                ll_store2(lo, o.x, o.y, p.ll_out_tag);
+                ll_store2(lo + 2, o.z, o.w, p.ll_out_tag);
+            }
         }
     }
     __syncthreads();
@@ -847,8 +916,13 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
             st->cur_len = L + 1;
             st->step = st_step + 1;
             st->has_last_scores = 1;
-            if (ld_state(&st->n_finished) >= B || L + 1 >= st_max_length) st->all_finished = 1;
+            const int fin_all = (ld_state(&st->n_finished) >= B || L + 1 >= st_max_length) ? 1 : 0;
+            if (fin_all) st->all_finished = 1;
             __threadfence();
+            if (p.ll_hdr) {        // token header of the dataflow megakernel: next cur_len, all-finished flag
+                ll_store(p.ll_hdr + 0, __int_as_float(L + 1), p.ll_out_tag);
+                ll_store(p.ll_hdr + 1, __int_as_float(fin_all), p.ll_out_tag);
+            }
         }
     }
 }

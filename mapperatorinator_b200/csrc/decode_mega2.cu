@@ -1,0 +1,506 @@
+// Dataflow token-loop megakernel: the same 98 dependent micro-phases per token as decode_mega.cu, the same device arithmetic
+// (gemv_dot, the attention unit's score / softmax / PV order, the fused logits chain), but NO grid barrier between them.
+//
+// Why: ncu + the clock64 timeline of round 1 showed the barrier kernel at 348 us / token is latency-bound, and 27 % of a token is the
+// barrier itself (98 x ~0.95 us = store drain + release atomic + acquire poll) with another ~0.3 us per phase for the activation load
+// that can only start after it.  Here every value that crosses CTAs is an 8-byte pair {fp32 bits | tag << 32} written by ONE 64-bit
+// store and polled by whoever needs it (NCCL's "LL" protocol): the consumer's load IS the wait, the producer never drains or
+// releases, and a CTA that has nothing to consume in a phase simply runs ahead.  tag = (step + 1) * 128 + phase + 1 is unique per
+// (token, phase), buffers are zeroed before every launch.
+//
+// Which CTA reads what, and why a buffer can be overwritten without a second copy: a version of a buffer is only overwritten by a
+// phase whose inputs transitively require EVERY reader of that version to have produced its own output first (e.g. x after out_proj
+// is read by the 128 CTAs that own rows of the cross-q projection; the next writer of x, the cross out_proj, needs the merged cross
+// attention, which needs every row of cross-q).  The full table is in DESIGN.md §4.1.
+//
+// The K/V rows appended to the cache are the one thing readers pick up long after the fact (next token onwards) through plain
+// ld.cg: their writer fences right after the plain stores (hidden: that warp then waits for the attention phase anyway) and the
+// NEWEST row travels as tagged pairs (`kvnew`) like every other same-token value.
+//
+// Every wait is bounded; on a timeout the error flag is raised, every other wait sees it and the launch drains.
+#include "common.cuh"
+#include "kernels.h"
+#include "decode_device.cuh"
+
+namespace mb200 {
+
+namespace {
+
+constexpr int M2_THREADS = SAMPLE_THREADS;              // 512
+constexpr int M2_WARPS = M2_THREADS / 32;
+constexpr int M2_NB_MAX = 2;
+constexpr int M2_XS_FLOATS = M2_NB_MAX * 3072;
+constexpr int M2_XRAW_FLOATS = M2_NB_MAX * 1024;
+constexpr int M2_PART = 66;                             // pairs per split partial: o[64], m, l
+
+struct __align__(16) M2Smem {
+    float wbuf[2][MEGA_WBUF_FLOATS];
+    union {
+        float xs[M2_XS_FLOATS];
+        SampleSmem sample;
+        struct { float sc[128]; float red[4][64]; float stat[2]; float qs[64]; } attn;
+    } u;
+    float xraw[M2_XRAW_FLOATS];                 // raw residual stream as of this CTA's last LayerNorm staging (residual source of its rows)
+    Mega2Phase phase[2];
+    SampleParams sample_params;
+    int ctrl[8];                                // cur_len, all_finished, error, prompt_len, encoder slots
+    float ln_red[32];
+    unsigned long long mbar[2];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    unsigned long long pol;      // weights stream through L2 once per token: evict-first keeps the small hot set (exchange buffers, K/V) resident
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cta_rows(int N, int cta, int rpc, int& r0, int& r1) {
+    r0 = min(N, cta * rpc);
+    r1 = min(N, r0 + rpc);
+}
+__device__ __forceinline__ void prefetch_weights(const float* W, long long ldw, int N, int K, float* dst, unsigned long long* bar, int cta, int rpc) {
+    int r0, r1;
+    cta_rows(N, cta, rpc, r0, r1);
+    const unsigned bytes = (unsigned)(r1 - r0) * (unsigned)K * 4u;
+    if (bytes == 0) { mbar_arrive(bar); return; }
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_g2s(dst, W + (long long)r0 * ldw, bytes, bar);
+}
+__device__ __forceinline__ bool wait_weights(unsigned long long* bar, unsigned parity, int* error_flag) {
+    for (long long spin = 0; spin < (1ll << 24); ++spin)
+        if (mbar_try_wait(bar, parity)) return true;
+    atomicCAS(error_flag, 0, 2);
+    return false;
+}
+
+__device__ __forceinline__ unsigned ll_tag(int step, int pi) { return (unsigned)((step + 1) * 128 + pi + 1); }
+
+__device__ __forceinline__ ll_t* ll_buf(const MegaLL& ll, int sel) {
+    switch (sel) {
+        case LL_X: return ll.x;
+        case LL_Q: return ll.q;
+        case LL_K: return ll.kvnew;
+        case LL_V: return ll.kvnew;
+        case LL_ATT: return ll.att;
+        case LL_H: return ll.h;
+        case LL_LOGITS: return ll.logits;
+        default: return nullptr;
+    }
+}
+
+// ---- activation staging ---------------------------------------------------------------------------------------------------------
+// LayerNorm prologue over the tagged residual stream: the reduction structure of gemv_stage_x (chunk of 32 float4 per warp, 8 chunk
+// partials per row reduced by a fixed tree), operands polled instead of loaded; the raw values are kept in `xraw` (this CTA adds them
+// back as the residual of the rows it owns two phases later, so the residual needs no second trip through L2).
+template <int NB>
+__device__ __forceinline__ void m2_stage_ln(const GemvParams& p, const ll_t* ll_in, unsigned tag, float* xs, float* xraw, float* red, int tid, int* err) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int K = p.K, K4 = K >> 2;
+    constexpr int RG = M2_WARPS / 8;                   // rows staged per round (16 warps: 2)
+    const float inv = 1.0f / (float)K;
+    for (int g0 = 0; g0 < NB; g0 += RG) {
+        const int rl = warp >> 3, bb = g0 + rl, c0 = warp & 7;
+        const bool row_ok = bb < NB && bb < p.B;
+        const int idx = c0 * 32 + lane;
+        const bool ok = row_ok && idx < K4;
+        float4 v = make_float4(0, 0, 0, 0), lw = v, lb = v;
+        if (ok) {
+            lw = __ldg(reinterpret_cast<const float4*>(p.ln_w) + idx);
+            lb = __ldg(reinterpret_cast<const float4*>(p.ln_b) + idx);
+            v = ll_wait4(ll_in + (long long)bb * K + idx * 4, tag, err);
+            reinterpret_cast<float4*>(xraw + bb * K)[idx] = v;
+        }
+        const float sc = warp_sum((v.x + v.y) + (v.z + v.w));
+        if (lane == 0) red[rl * 8 + c0] = sc;
+        __syncthreads();
+        const float* r = red + rl * 8;
+        const float mean = (((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))) * inv;
+        float q = 0.f;
+        if (ok) {
+            const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+            q = (a * a + b * b) + (c * c + d * d);
+        }
+        q = warp_sum(q);
+        if (lane == 0) red[RG * 8 + rl * 8 + c0] = q;
+        __syncthreads();
+        if (bb < NB && idx < K4) {
+            const float* r2 = red + RG * 8 + rl * 8;
+            const float rstd = rsqrtf((((r2[0] + r2[1]) + (r2[2] + r2[3])) + ((r2[4] + r2[5]) + (r2[6] + r2[7]))) * inv + p.eps);
+            float4 o = make_float4(0, 0, 0, 0);
+            if (row_ok) {
+                o.x = (v.x - mean) * rstd * lw.x + lb.x; o.y = (v.y - mean) * rstd * lw.y + lb.y;
+                o.z = (v.z - mean) * rstd * lw.z + lb.z; o.w = (v.w - mean) * rstd * lw.w + lb.w;
+            }
+            reinterpret_cast<float4*>(xs + bb * K)[idx] = o;
+        }
+    }
+}
+
+// chunk partials of warps that hold no chunk (c0 >= K4 / 32) must read as zero: the fixed tree always adds eight of them
+__device__ __forceinline__ void m2_clear_ln_red(float* red, int tid) {
+    if (tid < 32) red[tid] = 0.f;
+}
+
+template <int NB>
+__device__ __forceinline__ void m2_stage_plain(const GemvParams& p, const ll_t* ll_in, unsigned tag, float* xs, int tid, int* err) {
+    const int K4 = p.K >> 2;
+    for (int e = tid; e < NB * K4; e += M2_THREADS) {
+        const int bb = e / K4, c = e - bb * K4;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (bb < p.B) v = ll_wait4(ll_in + (long long)bb * p.K + c * 4, tag, err);
+        reinterpret_cast<float4*>(xs)[e] = v;
+    }
+}
+
+// ---- attention unit -------------------------------------------------------------------------------------------------------------
+// (split s, head h, row r) exactly like decode_attention_body<16>: the same score chains, the same per-warp softmax statistics, the same
+// four PV accumulation chains — only the operand sources differ: q and the newest K/V row are polled from the exchange buffers, the
+// result leaves as tagged pairs (merged heads when one split covers the context, else a split partial that the split-0 CTA merges).
+__device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const MegaLL& ll, bool is_self, int s, int h, int r, int slot, int L, int P,
+                                                  unsigned in_tag, unsigned out_tag, float* sc, float (*red)[64], float* stat, int tid,
+                                                  AttnRegs<M2_WARPS>& R, int* err) {
+    constexpr int NW = M2_WARPS;
+    constexpr int SC_ITERS = AttnRegs<NW>::SC_ITERS, PV_PRE = AttnRegs<NW>::PV_PRE;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int d = p.H * 64;
+    const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
+    const int nk = k_end - k_begin;
+    const int newest = is_self ? (L - 1 - k_begin) : -1;           // index inside this split of the key appended by THIS token (self only)
+    ll_t* part = ll.part + (((long long)r * p.H + h) * ll.max_splits + s) * M2_PART;
+    ll_t* att = ll.att + (long long)r * d + h * 64;
+    if (nk <= 0) {                                                 // empty split (uniform across the CTA)
+        if (p.n_splits == 1) { if (tid < 64) ll_store(att + tid, 0.f, out_tag); return; }
+        if (tid < 64) ll_store(part + tid, 0.f, out_tag);
+        if (tid == 0) { ll_store(part + 64, -INFINITY, out_tag); ll_store(part + 65, 0.f, out_tag); }
+        stat[0] = -INFINITY; stat[1] = 0.f;
+        return;
+    }
+    const int tok = (int)p.tok_stride;
+    const float* vb = p.vc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
+    const int sub = lane & 7, kq = lane >> 3;
+    // q: the only operand every lane needs from the previous phase
+    const float4 q0 = ll_wait4(ll.q + (long long)r * d + h * 64 + sub * 8, in_tag, err);
+    const float4 q1 = ll_wait4(ll.q + (long long)r * d + h * 64 + sub * 8 + 4, in_tag, err);
+    if (newest >= 0 && newest < nk) {                              // the appended key / value of this token arrive as tagged pairs
+        const ll_t* kn = ll.kvnew + (long long)r * 2 * d + h * 64;
+        const ll_t* vn = kn + d;
+#pragma unroll
+        for (int it = 0; it < SC_ITERS; ++it) {
+            const int kk = it * 4 * NW + warp * 4 + kq;
+            if (kk == newest) { R.ka[it] = ll_wait4(kn + sub * 8, in_tag, err); R.kb4[it] = ll_wait4(kn + sub * 8 + 4, in_tag, err); R.kvalid[it] = 1; }
+        }
+        if (warp < 4) {
+#pragma unroll
+            for (int i = 0; i < PV_PRE; ++i)
+                if (warp + 4 * i == newest) R.vpre[i] = ll_wait2(vn + lane * 2, in_tag, err);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < SC_ITERS; ++it) {
+        const int kk = it * 4 * NW + warp * 4 + kq;
+        const float4 a = R.ka[it], b = R.kb4[it];
+        float dd = q0.x * a.x;
+        dd = fmaf(q0.y, a.y, dd); dd = fmaf(q0.z, a.z, dd); dd = fmaf(q0.w, a.w, dd);
+        dd = fmaf(q1.x, b.x, dd); dd = fmaf(q1.y, b.y, dd); dd = fmaf(q1.z, b.z, dd); dd = fmaf(q1.w, b.w, dd);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 1);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 2);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 4);
+        if (kk < nk && sub == 0) sc[kk] = R.kvalid[it] ? dd : -INFINITY;
+    }
+    __syncthreads();
+    if (warp < 4) {
+        float pv[4];
+        float m = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = lane + 32 * t;
+            pv[t] = i < nk ? sc[i] : -INFINITY;
+            m = fmaxf(m, pv[t]);
+        }
+        m = warp_max(m);
+        float l = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = lane + 32 * t;
+            pv[t] = (i < nk && pv[t] != -INFINITY) ? expf(pv[t] - m) : 0.f;
+            if (i < nk) l += pv[t];
+        }
+        l = warp_sum(l);
+        if (tid == 0) { stat[0] = m; stat[1] = l; }
+        float2 o = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < PV_PRE; ++i) {
+            const int kk = warp + 4 * i;
+            const float pk = __shfl_sync(0xffffffffu, pv[i >> 3], kk & 31);
+            if (kk < nk) {
+                o.x = fmaf(pk, R.vpre[i].x, o.x);
+                o.y = fmaf(pk, R.vpre[i].y, o.y);
+            }
+        }
+        if (nk > 64) {
+#pragma unroll
+            for (int t = 2; t < 4; ++t) {
+                float2 vv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kk = 32 * t + warp + 4 * i;
+                    vv[i] = make_float2(0.f, 0.f);
+                    if (kk < nk) vv[i] = kk == newest ? ll_wait2(ll.kvnew + (long long)r * 2 * d + d + h * 64 + lane * 2, in_tag, err) : ldcg2(vb + kk * tok + lane * 2);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kk = 32 * t + warp + 4 * i;
+                    const float pk = __shfl_sync(0xffffffffu, pv[t], kk & 31);
+                    if (kk < nk) {
+                        o.x = fmaf(pk, vv[i].x, o.x);
+                        o.y = fmaf(pk, vv[i].y, o.y);
+                    }
+                }
+            }
+        }
+        red[warp][lane * 2] = o.x;
+        red[warp][lane * 2 + 1] = o.y;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const float v = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        if (p.n_splits == 1) {
+            // one split holds the whole context: the merge degenerates to o / l (w = exp(m - m) = 1: the same bits as the general path)
+            const float num = fmaf(1.f, v, 0.f), den = fmaf(1.f, stat[1], 0.f);
+            ll_store(att + tid, (stat[1] > 0.f && den > 0.f) ? num / den : 0.f, out_tag);
+        } else {
+            ll_store(part + tid, v, out_tag);
+            if (tid == 0) { ll_store(part + 64, stat[0], out_tag); ll_store(part + 65, stat[1], out_tag); }
+        }
+    }
+}
+
+// merge of the S split partials of (row r, head h) by the CTA that computed split 0: splits visited in index order,
+// out = sum_s w_s o_s / sum_s w_s l_s with w_s = exp(m_s - max m) — decode_attention_merge's arithmetic, operands polled
+__device__ __forceinline__ void m2_attention_merge(const DecAttnParams& p, const MegaLL& ll, int h, int r, unsigned tag, int tid, int* err) {
+    if (tid >= 64) return;
+    const int S = p.n_splits, d = p.H * 64;
+    const ll_t* base = ll.part + ((long long)r * p.H + h) * ll.max_splits * M2_PART;
+    float num = 0.f, den = 0.f;
+    if (S <= 8) {
+        float2 mv[8]; float ov[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            mv[s] = make_float2(-INFINITY, 0.f); ov[s] = 0.f;
+            if (s < S) { mv[s] = ll_wait2(base + (long long)s * M2_PART + 64, tag, err); ov[s] = ll_wait1(base + (long long)s * M2_PART + tid, tag, err); }
+        }
+        float mmax = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) if (s < S) mmax = fmaxf(mmax, mv[s].x);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            if (s < S && mv[s].y > 0.f) {
+                const float w = expf(mv[s].x - mmax);
+                num = fmaf(w, ov[s], num);
+                den = fmaf(w, mv[s].y, den);
+            }
+        }
+    } else {
+        float mmax = -INFINITY;
+#pragma unroll 1
+        for (int s = 0; s < S; ++s) mmax = fmaxf(mmax, ll_wait2(base + (long long)s * M2_PART + 64, tag, err).x);
+#pragma unroll 1
+        for (int s = 0; s < S; ++s) {
+            const float2 mv = ll_wait2(base + (long long)s * M2_PART + 64, tag, err);
+            const float ov = ll_wait1(base + (long long)s * M2_PART + tid, tag, err);
+            if (mv.y > 0.f) {
+                const float w = expf(mv.x - mmax);
+                num = fmaf(w, ov, num);
+                den = fmaf(w, mv.y, den);
+            }
+        }
+    }
+    ll_store(ll.att + (long long)r * d + h * 64 + tid, den > 0.f ? num / den : 0.f, tag);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Params mp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    M2Smem& sm = *reinterpret_cast<M2Smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int d = mp.d_model;
+    int* const err = mp.error_flag;
+
+    if (tid == 0) {
+        sm.sample_params = mp.sample;
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    m2_clear_ln_red(sm.ln_red, tid);
+    __syncthreads();
+    unsigned int g_idx = 0;          // running index of GEMV phases (selects weight buffer + mbarrier parity)
+    if (tid == 0) {
+        const MegaPhase* f = &mp.phases[0].base;
+        prefetch_weights(f->g.W, f->g.ldw, f->g.N, f->g.K, sm.wbuf[0], &sm.mbar[0], cta, (f->g.N + G - 1) / G);
+    }
+    // CTA 0 publishes the residual stream left by the prefill (plain memory, written by an earlier kernel) and the first token header
+    // under the tag the first phase of step 0 expects: "last phase of step -1"
+    if (cta == 0) {
+        const unsigned t0 = ll_tag(-1, mp.n_phases - 1);
+        for (int i = tid; i < mp.rows * d; i += M2_THREADS) ll_store(mp.ll.x + i, mp.x_in[i], t0);
+        if (tid == 0) {
+            ll_store(mp.ll.hdr + 0, __int_as_float(ld_state(&mp.st->cur_len)), t0);
+            ll_store(mp.ll.hdr + 1, __int_as_float(ld_state(&mp.st->all_finished)), t0);
+        }
+    }
+    {
+        const int* src = reinterpret_cast<const int*>(&mp.phases[0]);
+        int* dst = reinterpret_cast<int*>(&sm.phase[0]);
+        for (int i = tid; i < (int)(sizeof(Mega2Phase) / 4); i += M2_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    int cur = 0;
+    AttnRegs<M2_WARPS> areg;
+
+    for (int step = 0; step < mp.max_steps; ++step) {
+        if (tid == 0) {      // token header: written by the selection phase of the previous token (or the prologue above)
+            const unsigned th = ll_tag(step - 1, mp.n_phases - 1);
+            sm.ctrl[0] = __float_as_int(ll_wait1(mp.ll.hdr + 0, th, err));
+            sm.ctrl[1] = __float_as_int(ll_wait1(mp.ll.hdr + 1, th, err));
+            sm.ctrl[2] = *reinterpret_cast<volatile int*>(err);
+            sm.ctrl[3] = ld_state(&mp.st->prompt_len);
+            sm.ctrl[4] = mp.row_slot[0]; sm.ctrl[5] = mp.rows > 1 ? mp.row_slot[1] : 0;
+        }
+        __syncthreads();
+        const int cur_pos = sm.ctrl[0] - 1, fin = sm.ctrl[1], e = sm.ctrl[2], P = sm.ctrl[3];
+        if (fin || e) break;
+        for (int pi = 0; pi < mp.n_phases; ++pi) {
+            const Mega2Phase& ph2 = sm.phase[cur];
+            const MegaPhase& ph = ph2.base;
+            const unsigned in_tag = pi == 0 ? ll_tag(step - 1, mp.n_phases - 1) : ll_tag(step, pi - 1);
+            const unsigned out_tag = ll_tag(step, pi);
+            // next phase's descriptor: global -> shared asynchronously, drained before the end-of-phase CTA barrier
+            constexpr int DESC_WORDS = (int)(sizeof(Mega2Phase) / 4);
+            for (int i = tid; i < DESC_WORDS; i += M2_THREADS) {
+                const int* src = reinterpret_cast<const int*>(&mp.phases[pi + 1 < mp.n_phases ? pi + 1 : 0]) + i;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(reinterpret_cast<int*>(&sm.phase[cur ^ 1]) + i)), "l"(src) : "memory");
+            }
+            if (ph.kind == 0) {
+                const GemvParams& g = ph.g;
+                const int buf = g_idx & 1;
+                int r0, r1;
+                cta_rows(g.N, cta, ph.rpc, r0, r1);
+                // bias of this warp's rows: lane j*NB + b holds it for the warp's j-th row (fetched while the input is still on its way)
+                float bias_pref = 0.f;
+                {
+                    const int n = r0 + warp + (lane / NB) * M2_WARPS;
+                    if (n < r1 && g.bias) bias_pref = __ldg(g.bias + n);
+                }
+                if (r0 < r1) {
+                    const ll_t* in = ll_buf(mp.ll, ph2.in_sel);
+                    if (g.xmode == X_LAYERNORM) m2_stage_ln<NB>(g, in, in_tag, sm.u.xs, sm.xraw, sm.ln_red, tid, err);
+                    else m2_stage_plain<NB>(g, in, in_tag, sm.u.xs, tid, err);
+                }
+                __syncthreads();
+                // the next GEMV's weight slice is requested only now (after this phase's small latency-critical loads), by the last warp
+                if (tid == M2_THREADS - 32) prefetch_weights(ph.nx_W, ph.nx_ldw, ph.nx_N, ph.nx_K, sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, ph.nx_rpc);
+                wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err);
+                int j = 0;
+#pragma unroll 1
+                for (int n = r0 + warp; n < r1; n += M2_WARPS, ++j) {
+                    const float bias_v = __shfl_sync(0xffffffffu, bias_pref, (j * NB) & 31);
+                    const int si = (int)(g.nseg > 1 && n >= g.seg[1].n_begin) + (int)(g.nseg > 2 && n >= g.seg[2].n_begin);
+                    const GemvSeg& sg = g.seg[si];
+                    const int osel = ph2.out_sel[si];
+                    const float mine = gemv_dot<NB, false>(g.K, sm.wbuf[buf] + (long long)(n - r0) * g.K, sm.u.xs, lane);
+                    if (lane < NB && lane < g.B) {
+                        float v = mine;
+                        if (g.bias) v += bias_v;
+                        v = apply_act(v, sg.act) * sg.alpha;
+                        if (ph2.res_xraw) v += sm.xraw[lane * d + n];
+                        if (ph2.plain_out[si]) {
+                            sg.out[(long long)lane * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin)] = v;
+                            __threadfence();      // K/V cache rows are read by later tokens through plain loads: order them before this thread's next tagged store
+                        }
+                        if (osel != LL_NONE) {
+                            ll_t* out = ll_buf(mp.ll, osel);
+                            const long long width = osel == LL_K || osel == LL_V ? 2 * d : (osel == LL_H ? g.N : (osel == LL_LOGITS ? mp.V : d));
+                            const int col = osel == LL_V ? d + (n - sg.n_begin) : (n - sg.n_begin);
+                            ll_store(out + (long long)lane * width + col, v, out_tag);
+                        }
+                    }
+                }
+                ++g_idx;
+            } else if (ph.kind == 1) {
+                const DecAttnParams& a = ph.a;
+                const bool is_self = a.fixed_len == 0;
+                const int L = is_self ? cur_pos + 1 : a.fixed_len;
+                const int units = a.rows * a.H * a.n_splits;
+                for (int u = cta; u < units; u += G) {
+                    const int hr = ph.magic_ns ? (int)__umulhi((unsigned)u, ph.magic_ns) : u;
+                    const int s = u - hr * a.n_splits;
+                    const int r = ph.magic_h ? (int)__umulhi((unsigned)hr, ph.magic_h) : hr;
+                    const int h = hr - r * a.H;
+                    const int slot = a.row_slot ? sm.ctrl[4 + r] : r;
+                    // K/V of the cache first (they do not depend on this token's phases), q and the appended row are polled inside
+                    decode_attention_load<M2_WARPS>(a, s, h, r, slot, L, P, tid, areg);
+                    m2_attention_unit(a, mp.ll, is_self, s, h, r, slot, L, P, in_tag, out_tag, sm.u.attn.sc, sm.u.attn.red, sm.u.attn.stat, tid, areg, err);
+                    if (a.n_splits > 1 && s == 0) m2_attention_merge(a, mp.ll, h, r, out_tag, tid, err);
+                    __syncthreads();
+                }
+            } else {
+                if (cta < sm.sample_params.cfg->B) {
+                    if (tid == 0) { sm.sample_params.ll_in_tag = in_tag; sm.sample_params.ll_out_tag = out_tag; }
+                    __syncthreads();
+                    sample_body(sm.sample_params, cta, sm.u.sample);
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();                              // xs / attention scratch free for the next phase; the next descriptor has landed
+            cur ^= 1;
+        }
+    }
+    // drain the weight prefetch that is still in flight so no bulk copy outlives the CTA
+    wait_weights(&sm.mbar[g_idx & 1], (g_idx >> 1) & 1, err);
+}
+
+}  // namespace
+
+size_t mega2_smem_bytes() { return sizeof(M2Smem) + 128; }
+
+int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
+        int per_sm = 0;
+        MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel_ll<2>, M2_THREADS, mega2_smem_bytes()));
+        MB_REQUIRE(per_sm >= 1, "dataflow megakernel does not fit on an SM");
+        configured = true;
+    }
+    MB_REQUIRE(mp.rows >= 1 && mp.rows <= M2_NB_MAX, "megakernel handles 1 or 2 decoder rows");
+    MB_REQUIRE(mp.n_phases <= 126, "tag layout holds at most 126 phases per token");
+    MB_REQUIRE(mp.d_model <= 1024, "residual scratch holds d_model <= 1024");
+    Mega2Params p = mp;
+    void* args[] = {&p};
+    const void* fn = mp.rows == 1 ? (const void*)decode_megakernel_ll<1> : (const void*)decode_megakernel_ll<2>;
+    // Cooperative launch for its co-residency guarantee: every CTA polls values that other CTAs produce, so all of them must be resident.
+    MB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(M2_THREADS), args, mega2_smem_bytes(), stream));
+    ++g_launch_count;
+    return 0;
+}
+
+}  // namespace mb200

@@ -74,7 +74,11 @@ struct mb200_model {
     std::map<std::tuple<int, int, int, int>, int> prefill_seen;                                   // (rows, B, P, position rule)
     std::map<std::tuple<int, int, int, int>, std::pair<cudaGraphExec_t, long long>> prefill_graphs;   // -> graph + node count
     // persistent megakernel path
-    bool use_mega = true;
+    int use_mega = 2;                   // 0 = CUDA-graph replay per token, 1 = grid-barrier megakernel, 2 = dataflow (tagged-pair) megakernel
+    DevBuf ll_arena;                    // exchange buffers of the dataflow megakernel (rows <= 2)
+    MegaLL ll{};
+    size_t ll_bytes = 0;
+    std::map<std::tuple<int, int, int>, std::pair<DevBuf*, int>> mega2_phases;   // (rows, B, n_splits_self) -> device phase table
     int num_sms = 0;                    // 0 = no cooperative launch -> no megakernel
     int num_sms_phys = 0;
     DevBuf g_megasync;                  // [0] grid-barrier counter, [8] error flag
@@ -171,6 +175,7 @@ extern "C" void mb200_model_destroy(mb200_model* m) {
     for (auto& g : m->prefill_graphs) cudaGraphExecDestroy(g.second.first);
     m->gemm.destroy();
     for (auto& kv : m->mega_phases) delete kv.second.first;
+    for (auto& kv : m->mega2_phases) delete kv.second.first;
     for (auto& e : m->mega_ev) if (e) cudaEventDestroy(e);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     mel_plan_destroy(m->mel);
@@ -334,6 +339,18 @@ extern "C" int mb200_model_finalize(mb200_model* m) {
         MB_TRY(m->d_attn.ensure((size_t)m->max_rows * d * sizeof(float)));
         MB_TRY(m->d_ticket.ensure((size_t)m->max_rows * c.heads * sizeof(int)));
         MB_CUDA_CHECK(cudaMemset(m->d_ticket.p, 0, (size_t)m->max_rows * c.heads * sizeof(int)));
+    }
+    {   // exchange buffers of the dataflow megakernel: 8-byte {value | tag} pairs, two decoder rows
+        const int R2 = 2, max_splits = std::max((c.tgt_seq_len + 63) / 64, (c.src_seq_len / 2 + 63) / 64);
+        auto al = [](size_t n) { return (n + 15) & ~size_t(15); };
+        const size_t n_x = al((size_t)R2 * d), n_kv = al((size_t)R2 * 2 * d), n_h = al((size_t)R2 * f), n_l = al((size_t)R2 * c.vocab_size_out),
+                     n_p = al((size_t)R2 * c.heads * max_splits * 66), n_hdr = 16;
+        m->ll_bytes = (3 * n_x + n_kv + n_h + n_l + n_p + n_hdr) * 8;
+        MB_TRY(m->ll_arena.ensure(m->ll_bytes, true));
+        unsigned long long* b = m->ll_arena.as<unsigned long long>();
+        m->ll.x = b; b += n_x; m->ll.q = b; b += n_x; m->ll.att = b; b += n_x; m->ll.kvnew = b; b += n_kv; m->ll.h = b; b += n_h;
+        m->ll.logits = b; b += n_l; m->ll.part = b; b += n_p; m->ll.hdr = b;
+        m->ll.max_splits = max_splits;
     }
     m->finalized = true;
     return 0;
@@ -686,6 +703,68 @@ static int run_megakernel(mb200_model* m, int rows, int B, int n_splits_self, in
     return 0;
 }
 
+// The dataflow path: same phase list, each phase annotated with the exchange buffers it reads / writes.
+static int run_megakernel2(mb200_model* m, int rows, int B, int n_splits_self, int max_steps, cudaStream_t st) {
+    auto key = std::make_tuple(rows, B, n_splits_self);
+    auto it = m->mega2_phases.find(key);
+    if (it == m->mega2_phases.end()) {
+        std::vector<MegaPhase> phases;
+        MB_TRY(token_step(m, rows, B, n_splits_self, st, false, &phases));
+        std::vector<Mega2Phase> p2(phases.size());
+        const float *dx = m->d_x.as<float>(), *dq = m->d_q.as<float>(), *dh = m->d_h.as<float>(), *datt = m->d_attn.as<float>(),
+                    *dlog = m->d_logits.as<float>();
+        for (size_t i = 0; i < phases.size(); ++i) {
+            Mega2Phase& q = p2[i];
+            q = Mega2Phase{};
+            q.base = phases[i];
+            if (phases[i].kind != 0) continue;
+            const GemvParams& g = phases[i].g;
+            q.in_sel = g.xmode == X_LAYERNORM ? LL_X : (g.x == datt ? LL_ATT : (g.x == dh ? LL_H : LL_NONE));
+            MB_REQUIRE(q.in_sel != LL_NONE && (g.xmode != X_LAYERNORM || g.x == dx), "dataflow megakernel: unknown GEMV input buffer");
+            q.res_xraw = g.R != nullptr;
+            MB_REQUIRE(!g.R || g.R == dx, "dataflow megakernel: residual must be the residual stream");
+            for (int sgi = 0; sgi < g.nseg; ++sgi) {
+                const GemvSeg& sg = g.seg[sgi];
+                if (sg.pos_stride != 0) { q.out_sel[sgi] = sgi == 1 ? LL_K : LL_V; q.plain_out[sgi] = 1; MB_REQUIRE(sgi >= 1, "cache segment order"); }
+                else if (sg.out == dq) q.out_sel[sgi] = LL_Q;
+                else if (sg.out == dx) q.out_sel[sgi] = LL_X;
+                else if (sg.out == dh) q.out_sel[sgi] = LL_H;
+                else if (sg.out == dlog) q.out_sel[sgi] = LL_LOGITS;
+                else MB_REQUIRE(false, "dataflow megakernel: unknown GEMV output buffer");
+            }
+        }
+        DevBuf* buf = new DevBuf();
+        MB_TRY(buf->ensure(p2.size() * sizeof(Mega2Phase)));
+        MB_CUDA_CHECK(cudaMemcpy(buf->p, p2.data(), p2.size() * sizeof(Mega2Phase), cudaMemcpyHostToDevice));
+        it = m->mega2_phases.emplace(key, std::make_pair(buf, (int)p2.size())).first;
+    }
+    MB_TRY(m->g_megasync.ensure(64));
+    MB_CUDA_CHECK(cudaMemsetAsync(m->g_megasync.p, 0, 64, st));
+    MB_CUDA_CHECK(cudaMemsetAsync(m->ll_arena.p, 0, m->ll_bytes, st));        // tag 0 = "nothing here yet"
+    Mega2Params mp{};
+    mp.phases = it->second.first->as<Mega2Phase>(); mp.n_phases = it->second.second;
+    mp.sample = sample_params(m, rows); mp.st = m->g_state.as<GenState>();
+    mp.ll = m->ll; mp.error_flag = m->g_megasync.as<int>() + 8;
+    mp.sample.ll_logits = m->ll.logits; mp.sample.ll_x_out = m->ll.x; mp.sample.ll_hdr = m->ll.hdr; mp.sample.ll_err = mp.error_flag;
+    mp.max_steps = max_steps; mp.row_slot = m->g_rowslot.as<int>(); mp.x_in = m->d_x.as<float>();
+    mp.rows = rows; mp.d_model = m->cfg.d_model; mp.V = m->cfg.vocab_size_out;
+    if (!m->mega_ev[0]) { MB_CUDA_CHECK(cudaEventCreate(&m->mega_ev[0])); MB_CUDA_CHECK(cudaEventCreate(&m->mega_ev[1])); }
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 2, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaEventRecord(m->mega_ev[0], st));
+    MB_TRY(launch_megakernel2(mp, m->num_sms, st));
+    MB_CUDA_CHECK(cudaEventRecord(m->mega_ev[1], st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 1, m->g_megasync.as<int>() + 8, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 3, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        MB_CUDA_CHECK(cudaEventElapsedTime(&ms, m->mega_ev[0], m->mega_ev[1]));
+        m->mega_ms += ms; m->mega_launches += 1; m->mega_tokens += m->h_flag[3] - m->h_flag[2];
+    }
+    MB_REQUIRE(m->h_flag[1] == 0, m->h_flag[1] == 2 ? "dataflow megakernel: weight copy timed out" : "dataflow megakernel: a wait for tagged data timed out");
+    return 0;
+}
+
 static bool mega_eligible(const mb200_model* m, int rows) {
     if (!m->use_mega || rows > 2 || m->num_sms <= 0) return false;
     const auto& c = m->cfg;
@@ -814,7 +893,8 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
 
     // ---- token loop, persistent path: every remaining token in ONE cooperative launch ----
     if (mega_eligible(m, rows) && gp->max_length - (P + 1) > 0) {
-        MB_TRY(run_megakernel(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
+        if (m->use_mega == 2) MB_TRY(run_megakernel2(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
+        else MB_TRY(run_megakernel(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
         MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
         MB_CUDA_CHECK(cudaStreamSynchronize(st));
         const int Lm = *m->h_flag;
@@ -913,7 +993,7 @@ extern "C" int mb200_model_set_option(mb200_model* m, const char* name, int valu
         m->use_pdl = value != 0;
         return 0;
     }
-    if (!strcmp(name, "mega")) { m->use_mega = value != 0; return 0; }
+    if (!strcmp(name, "mega")) { m->use_mega = value; return 0; }
     if (!strcmp(name, "mega_trace")) {
         if (value) { MB_TRY(m->mega_trace.ensure(128 * 16 * 8)); MB_CUDA_CHECK(cudaMemset(m->mega_trace.p, 0, 128 * 16 * 8)); }
         return 0;

@@ -196,6 +196,11 @@ struct SampleParams {
     float* x_out; long long x_ld;                   // [rows, d_model] residual stream input of the next step
     int rows;
     float* dbg_scores;                              // parity hook, null in production: [B, V] scores the selection sees (-inf = removed)
+    // dataflow megakernel only (null otherwise): logits arrive as tagged pairs, and the next step's embedding + the token header leave
+    // as tagged pairs (see decode_mega2.cu)
+    const unsigned long long* ll_logits; unsigned ll_in_tag;
+    unsigned long long* ll_x_out; unsigned long long* ll_hdr; unsigned ll_out_tag;
+    int* ll_err;
 };
 int launch_sample(const SampleParams& p, int B, cudaStream_t stream, bool pdl);
 
@@ -223,6 +228,43 @@ struct MegaParams {
 };
 size_t mega_smem_bytes();
 int launch_megakernel(const MegaParams& mp, int grid, cudaStream_t stream);
+
+// ---- decode_mega2.cu: the DATAFLOW token-loop megakernel ----------------------------------------------------------------
+// Same phases, same arithmetic, no grid barrier: every value that crosses CTAs travels as an 8-byte {fp32 bits | tag << 32} pair
+// written by one 64-bit store and polled by its consumers, so the data IS the synchronisation (one L2 store + one L2 load between
+// producer and consumer instead of store-drain + release atomic + acquire poll + load).
+struct MegaLL {                                   // engine-owned exchange buffers, zeroed by the host before every launch (tag 0 = invalid)
+    unsigned long long* x;                        // [rows][d]      residual stream
+    unsigned long long* q;                        // [rows][d]      self / cross query
+    unsigned long long* kvnew;                    // [rows][2d]     k | v of the token being processed (also stored plainly into the cache)
+    unsigned long long* att;                      // [rows][d]      merged attention heads
+    unsigned long long* h;                        // [rows][ffn]    fc1 output
+    unsigned long long* logits;                   // [rows][V]
+    unsigned long long* part;                     // [rows][H][max_splits][66]  split-KV partials: o[64], m, l
+    unsigned long long* hdr;                      // [0] cur_len, [1] all_finished of the NEXT token (written by the selection phase)
+    int max_splits;
+};
+enum MegaLLSel : int { LL_NONE = 0, LL_X = 1, LL_Q = 2, LL_K = 3, LL_V = 4, LL_ATT = 5, LL_H = 6, LL_LOGITS = 7 };
+struct Mega2Phase {
+    MegaPhase base;                               // the barrier kernel's descriptor (weights, segments, attention geometry, prefetch chain)
+    int in_sel;                                   // GEMV input buffer: LL_X (LayerNorm prologue), LL_ATT, LL_H
+    int out_sel[3];                               // per output segment: which exchange buffer receives the tagged copy (LL_NONE = plain only)
+    int res_xraw;                                 // epilogue adds the residual from the raw x this CTA staged at the last LL_X input
+    int plain_out[3];                             // per segment: also store plainly through seg.out (the K/V cache)
+};
+struct Mega2Params {
+    const Mega2Phase* phases; int n_phases;
+    SampleParams sample;
+    GenState* st;
+    MegaLL ll;
+    int* error_flag;
+    int max_steps;
+    const int* row_slot;
+    const float* x_in;                            // [rows][d] plain residual stream left by the prefill's selection kernel
+    int rows, d_model, V;
+};
+size_t mega2_smem_bytes();
+int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream);
 
 // one-time per call: scan the prompt for the MonotonicTimeShift state (logit_processors.py:149-166)
 int launch_prompt_scan(const long long* ids, long long ids_ld, int B, int P, const unsigned char* vflags, int ts_start, int ts_end,

@@ -97,7 +97,7 @@ def test_song_decoder_equals_per_window_calls_full_dims(full, layout, seed):
     from mapperatorinator_b200.pipeline import SongDecoder, segment
     from mapperatorinator_b200.server import model_generate
     cfg, sd, model = full
-    n, new = 20, 24
+    n, new = 20, 32                      # 32 new tokens: window i > 0 then has the bench's 50-token prompt (18 + the last 32 ids)
     windows, _, _ = segment(_song(seed, 25.0), cfg)
     windows = windows[:n]
     prompt_fn, gk_fn = _bench_like(cfg, layout, n, new)
@@ -110,6 +110,7 @@ def test_song_decoder_equals_per_window_calls_full_dims(full, layout, seed):
         ids, _ = model_generate(model, layout, dict(inputs=windows[i:i + 1], decoder_input_ids=p, decoder_attention_mask=p.ne(0)), gk_fn(i, p.shape[1]))
         b.append(ids[0, p.shape[1]:].tolist())
     for i in range(n):
+        assert len(a[i]) == len(b[i]) == new
         assert a[i] == b[i], f"song {seed} window {i}: first differing token {next(j for j in range(new) if a[i][j] != b[i][j])}"
 
 

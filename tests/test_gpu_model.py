@@ -53,16 +53,19 @@ def test_teacher_forced_logits_left_padded(tiny, gen_gold):
     assert np.allclose(out.numpy()[:, ::3, ::37][r3], g[r3], rtol=1e-3, atol=3e-4)
 
 
-@pytest.mark.parametrize("path", ["megakernel", "graph", "graph_pdl"])
+MEGA_MODE = {"megakernel": 1, "dataflow": 2, "graph": 0, "graph_pdl": 0}
+
+
+@pytest.mark.parametrize("path", ["dataflow", "megakernel", "graph", "graph_pdl"])
 @pytest.mark.parametrize("case", list(cases.generate_cases()))
 def test_greedy_generate_bit_exact(tiny, layout, gen_gold, case, path):
-    """Both token-loop implementations (persistent megakernel; CUDA-graph replay, with and without programmatic dependent
-    launch) must reproduce the reference's greedy ids exactly: prompts with left padding, look-back bias, natural EOS stop,
-    time-shift bias + batch-row-0 conditional temperature, classifier-free guidance."""
+    """Every token-loop driver (dataflow megakernel = tagged-pair exchange, no grid barrier; grid-barrier megakernel; CUDA-graph
+    replay, with and without programmatic dependent launch) must reproduce the reference's greedy ids exactly: prompts with left
+    padding, look-back bias, natural EOS stop, time-shift bias + batch-row-0 conditional temperature, classifier-free guidance."""
     from mapperatorinator_b200.server import model_generate
     from oracle import generate as go
     flavour, cfg, sd, model = tiny
-    model.engine.set_option("mega", 1 if path == "megakernel" else 0)
+    model.engine.set_option("mega", MEGA_MODE[path])
     model.engine.set_option("pdl", 1 if path == "graph_pdl" else 0)
     prompt, neg, gk, seed = cases.generate_cases()[case]
     B = prompt.shape[0]
@@ -72,7 +75,7 @@ def test_greedy_generate_bit_exact(tiny, layout, gen_gold, case, path):
     try:
         got, gstats = model_generate(model, layout, dict(mk), dict(gk))
     finally:
-        model.engine.set_option("mega", 1)
+        model.engine.set_option("mega", 2)
         model.engine.set_option("pdl", 0)
     assert got.shape == want.shape, (got.shape, want.shape)
     if not torch.equal(got, want):
@@ -82,7 +85,7 @@ def test_greedy_generate_bit_exact(tiny, layout, gen_gold, case, path):
     assert np.array_equal(got.numpy(), gen_gold[f"{flavour}/{case}/ids"]), "differs from the reference fixture"
 
 
-@pytest.mark.parametrize("path", ["megakernel", "graph"])
+@pytest.mark.parametrize("path", ["dataflow", "megakernel", "graph"])
 @pytest.mark.parametrize("case", list(cases.long_context_cases()))
 def test_greedy_generate_long_context(tiny, layout, gen_gold, case, path):
     """Contexts beyond 128 tokens switch the self-attention cache to 64-key splits merged by the last-arriving split (3 splits at
@@ -96,11 +99,11 @@ def test_greedy_generate_long_context(tiny, layout, gen_gold, case, path):
     prompt, gk, seed = cases.long_context_cases()[case]
     mk = dict(inputs=cases.model_pcm(cfg, 2, seed), decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0))
     want, _ = go.model_generate(sd, cfg, layout, dict(mk), dict(gk))
-    model.engine.set_option("mega", 1 if path == "megakernel" else 0)
+    model.engine.set_option("mega", MEGA_MODE[path])
     try:
         got, _ = model_generate(model, layout, dict(mk), dict(gk))
     finally:
-        model.engine.set_option("mega", 1)
+        model.engine.set_option("mega", 2)
     assert got.shape == want.shape
     if not torch.equal(got, want):
         r, c = (got != want).nonzero()[0].tolist()
