@@ -136,7 +136,7 @@ class ClockSampler:
 def workload_config(n_windows: int, dit: bool, songs_per_gpu: int = 1) -> dict:
     cfg = {"workload": "osuT5 v29 full-song inference, 180 s synthetic 16 kHz audio, sequential sliding windows (configs[1], SURVEY 8d 2a)"
                        + (" + osu_diffusion DiT-B 100-step position refinement (configs[2], SURVEY 8d 3)" if dit else ""),
-           "windows": n_windows, "new_tokens_per_window": NEW_TOKENS, "decode": "greedy, min_new_tokens=64", "batch": 1,
+           "windows": n_windows, "new_tokens_per_window": NEW_TOKENS, "decode": "greedy, min_new_tokens=64", "batch": songs_per_gpu,
            "weights": "seeded random init, whisper-small dims (213M) + DiT-B (131M), fp32", "songs_per_gpu_per_step": songs_per_gpu,
            "l2": "inputs larger than L2: each token streams the 464 MB fp32 decoder (L2 = 126 MB)"}
     if dit:
@@ -254,6 +254,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--song-seed", type=int, default=0, help="rank r decodes synth_song(song_seed + r)")
+    ap.add_argument("--songs-per-gpu", type=int, default=1,
+                    help="songs decoded in lock-step per GPU per step (BASELINE configs[3]: 8 -> 64 songs on 8 GPUs); rank r takes songs "
+                         "song_seed + r*S .. +S-1; window i of all S songs is one batch-S generate() call")
     ap.add_argument("--dit", type=int, default=1, help="1 = include the osu_diffusion stage the metric names (default), 0 = decode only")
     ap.add_argument("--cpu-windows", type=int, default=4, help="windows per CPU step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -284,18 +287,22 @@ def main() -> None:
     cfg = v29_model_config()
     layout = TokenLayout.from_json(os.path.join(ROOT, "tests", "golden", "tokenizer_v29.json"))
     sd = init_model_state_dict(cfg, 0)                       # same weights on every rank
-    song_id = args.song_seed + rank
-    windows, _, _ = segment(synth_song(song_id), cfg)        # rank r decodes song song_seed + r
+    S = max(1, args.songs_per_gpu)
+    song_ids = [args.song_seed + rank * S + k for k in range(S)]      # rank r decodes songs song_seed + r*S .. + S-1
+    song_id = song_ids[0]
+    songs = [segment(synth_song(sid), cfg)[0] for sid in song_ids]
     if args.windows:
-        windows = windows[:args.windows]
+        songs = [w[:args.windows] for w in songs]
+    windows = songs[0]
     n_windows = windows.shape[0]
-    model = B200Mapperatorinator(cfg, sd, max_windows=n_windows, max_batch=2, device=dev)
+    model = B200Mapperatorinator(cfg, sd, max_windows=S * n_windows, max_batch=max(2, S), device=dev)
     if args.pdl:
         model.engine.set_option("pdl", 1)
     model.engine.set_option("mega", args.mega)
     song = SongDecoder(model, layout)
-    pinned = windows.pin_memory()
-    resident = windows.to(dev)
+    all_windows = torch.stack(songs)                                   # (S, n_windows, samples)
+    pinned = all_windows.pin_memory()
+    resident = all_windows.to(dev)
     lib = _lib.load()
     lib.mb200_set_tensor_cores(int(args.tc))
     dit = None
@@ -303,15 +310,16 @@ def main() -> None:
         dc = dit_b_config(DIT_CLASSES)
         dsd = init_dit_state_dict(dc, 1)
         dit = B200DiT(dc, dsd, max_seq_len=DIT_GEOMETRY["max_seq_len"], device=dev)
-        seq_x, seq_c, y, y_null = synth_hit_objects(song_id)
-        hit_pinned = [t.pin_memory() for t in (seq_x, seq_c, y, y_null)]
-        hit_resident = [t.to(dev) for t in (seq_x, seq_c, y, y_null)]
+        hits = [synth_hit_objects(sid) for sid in song_ids]
+        seq_x, seq_c, y, y_null = hits[0]
+        hit_pinned = [[t.pin_memory() for t in h] for h in hits]
+        hit_resident = [[t.to(dev) for t in h] for h in hits]
         noise_gen = torch.Generator(device=dev)
 
-    def refine(inputs):
+    def refine(inputs, sid):
         """Stage (iii) through the public API; per-step noise drawn on the device from a seeded generator (the reference draws
         `th.randn_like` per step, gaussian_diffusion.py:454)."""
-        noise_gen.manual_seed(77 + song_id)
+        noise_gen.manual_seed(77 + sid)
         noise = [torch.randn(DIT_STEPS, 2, 2, b - a, device=dev, generator=noise_gen) for a, b in dit_chunks()]
         return sample_sequence(dit, inputs[0], inputs[1], inputs[2], inputs[3], 1.0, step_noise=noise, **DIT_GEOMETRY)
 
@@ -320,28 +328,34 @@ def main() -> None:
     def step_resident():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        song.encode_song(resident)
+        for k in range(S):
+            song.encode_song(resident[k], slot_begin=k * n_windows)
         ev[1].record()
-        streams = song.decode_windows(n_windows, prompt_for, lambda i: gen_kwargs(i, n_windows, 18 if i == 0 else 50))
+        if S == 1:
+            streams = [song.decode_windows(n_windows, prompt_for, lambda i: gen_kwargs(i, n_windows, 18 if i == 0 else 50))]
+        else:
+            streams = song.decode_songs(S, n_windows, lambda k, i, st: prompt_for(i, st), lambda i: gen_kwargs(i, n_windows, 18 if i == 0 else 50))
         ev[2].record()
-        pos = refine(hit_resident) if dit is not None else None
+        pos = [refine(hit_resident[k], song_ids[k]) for k in range(S)] if dit is not None else None
         ev[3].record()
         if world > 1:
-            gather_token_streams([sum(streams, [])], [rank])
+            gather_token_streams([sum(st, []) for st in streams], song_ids)
         step_resident.events.append(ev)
-        return sum(len(s) for s in streams), streams, pos
+        return sum(len(w) for st in streams for w in st), streams, pos
     step_resident.events = []
 
     def step_e2e():
-        streams, toks = [], 0
+        streams, toks = [[] for _ in range(S)], 0
         for i in range(n_windows):
-            prompt = torch.tensor([prompt_for(i, streams)])
-            ids, stats = model_generate(model, layout, dict(inputs=pinned[i:i + 1], decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0)),
+            prompt = torch.tensor([prompt_for(i, streams[k]) for k in range(S)])
+            ids, stats = model_generate(model, layout, dict(inputs=pinned[:, i], decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0)),
                                         gen_kwargs(i, n_windows, prompt.shape[1]))
-            streams.append(ids[0, prompt.shape[1]:].tolist()); toks += stats["generated_tokens"]
-        pos = refine(hit_pinned).cpu() if dit is not None else None
+            for k in range(S):
+                streams[k].append(ids[k, prompt.shape[1]:].tolist())
+            toks += stats["generated_tokens"]
+        pos = [refine(hit_pinned[k], song_ids[k]).cpu() for k in range(S)] if dit is not None else None
         if world > 1:
-            gather_token_streams([sum(streams, [])], [rank])
+            gather_token_streams([sum(st, []) for st in streams], song_ids)
         return toks, streams, pos
 
     def timed(fn, steps, warmup):
@@ -386,10 +400,16 @@ def main() -> None:
     e2e_steps = max(1, args.steps // 2)
     ms_e2e, toks_e2e, _, streams2, pos2 = timed(step_e2e, e2e_steps, 1)
     # the two arms must emit the same tokens (and positions): reported, not asserted, so every rank always prints / exits cleanly
-    div = first_stream_divergence(streams, streams2)
+    div = None
+    for k in range(S):
+        dk = first_stream_divergence(streams[k], streams2[k])
+        if dk is not None:
+            div = dict(dk, song=song_ids[k]); break
     consistency = {"resident_equals_e2e": div is None, "first_divergence": div}
     if dit is not None:
-        consistency["positions_max_abs_diff"] = float((pos.cpu() - pos2).abs().max())
+        consistency["positions_max_abs_diff"] = max(float((a.cpu() - b).abs().max()) for a, b in zip(pos, pos2))
+    all_streams, all_streams2 = streams, streams2
+    streams, streams2 = all_streams[0], all_streams2[0]                # song 0 of this rank feeds the CPU / oracle checks below
     if world > 1:
         flag = torch.tensor([0 if div is None else 1], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.SUM)
@@ -452,7 +472,7 @@ def main() -> None:
         if args.oracle_check != "none":
             which = list(range(n_windows)) if args.oracle_check == "full" else list(range(0, n_windows, 8))
             oracle_check = oracle_song_check(cfg, layout, sd, windows, streams, which)
-            if div is not None:      # which arm disagrees with the oracle at the point where the two arms part?
+            if div is not None and div["song"] == song_id:      # which arm disagrees with the oracle at the point where the two arms part?
                 w = div["window"]
                 consistency["oracle_on_e2e_window"] = oracle_song_check(cfg, layout, sd, windows, streams2[:w + 1] + streams[w + 1:], [w])
         if dit is not None:
@@ -475,17 +495,17 @@ def main() -> None:
                                      model_kwargs=mk, step_noise=noise.to(dev)).cpu()
             err = float((got - ref).abs().max())
             dit_parity = {"chunk_points": Tp, "steps": DIT_STEPS, "max_abs_err": err, "tolerance": 1e-3, "ok": bool(err <= 1e-3), "oracle_seconds": t_ref}
-    h2d = n_windows * cfg.samples_per_window * 4
-    d2h = n_windows * (50 + NEW_TOKENS) * 8
+    h2d = S * n_windows * cfg.samples_per_window * 4
+    d2h = S * n_windows * (50 + NEW_TOKENS) * 8
     if dit is not None:
-        h2d += 4 * (2 * DIT_POINTS + dc.context_size * DIT_POINTS + 2 * DIT_CLASSES)
-        d2h += 4 * 2 * DIT_POINTS
+        h2d += S * 4 * (2 * DIT_POINTS + dc.context_size * DIT_POINTS + 2 * DIT_CLASSES)
+        d2h += S * 4 * 2 * DIT_POINTS
     tok_per_song = toks / args.steps / world
     decode_only_ms = stage_ms["encode"] + stage_ms["decode"]
     print(json.dumps({
         "metric": METRIC if dit is not None else "event tokens/sec end-to-end", "value": toks / (ms / 1000), "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(n_windows, dit is not None), "clocks": clocks,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(n_windows, dit is not None, S), "clocks": clocks,
         "e2e": {"value": toks_e2e / (ms_e2e / 1000), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "server.model_generate per window (host tensors in, CPU LongTensor out)"
                        + (" + diffusion.sample_sequence (host tensors in, CPU positions out)" if dit is not None else "")},
@@ -494,7 +514,8 @@ def main() -> None:
                                                    "(all windows) | DiT refinement (2 chunks x 100 steps)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "self_consistency": consistency, "oracle_check": oracle_check,
         "dit_parity": dit_parity, "pdl": bool(args.pdl), "tensor_cores": bool(args.tc), "song_seed": args.song_seed,
-        "token_stream_sha1": hashlib.sha1(json.dumps(streams).encode()).hexdigest()}))
+        "token_stream_sha1": hashlib.sha1(json.dumps(streams).encode()).hexdigest(),
+        "token_stream_sha1_all_songs": hashlib.sha1(json.dumps(all_streams).encode()).hexdigest() if S > 1 else None}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -654,24 +654,56 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
     const bool suppress_eos = st_min_new > 0 && (L - st_prompt_len) < st_min_new;
 
     // (0)+(1): min_new_tokens EOS suppression, then classifier-free guidance on raw logits
+    if (p.ll_logits) {
+        // dataflow megakernel: logits arrive as tagged pairs; all of a thread's pairs are requested before the first tag is examined
+        constexpr int PER = VMAX / SAMPLE_THREADS;
+        float cond[PER];
+        for (int half = 0; half < (c.use_cfg ? 2 : 1); ++half) {      // conditional rows, then (CFG only) the unconditional rows
+            ll_t w[PER];
+            const ll_t* src = p.ll_logits + (long long)(half * B + b) * V;
+            long long spin = 0;
+            while (true) {
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const int v = tid + j * SAMPLE_THREADS;
+                    if (v < V) asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w[j]) : "l"(src + v) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const int v = tid + j * SAMPLE_THREADS;
+                    if (v < V) ok = ok && (unsigned)(w[j] >> 32) == p.ll_in_tag;
+                }
+                if (ok || !ll_spin_check(spin, p.ll_err)) break;
+            }
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int v = tid + j * SAMPLE_THREADS;
+                if (v < V) {
+                    const float x = __uint_as_float((unsigned)w[j]);
+                    if (half == 0) cond[j] = x;                            // first half = "conditional" in HF's processor
+                    if (half == 1 || !c.use_cfg) {
+                        const bool eos = (p.vflags[v] & VF_EOS) != 0;
+                        const float y = c.use_cfg ? x + (cond[j] - x) * c.cfg_scale : x;
+                        s[v] = (suppress_eos && eos) ? -INFINITY : y;
+                    }
+                }
+            }
+        }
+    } else {
     _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
         float x;
         const bool eos = (p.vflags[v] & VF_EOS) != 0;
         if (c.use_cfg) {
-            float cond, unc;                                                          // first half = "conditional" in HF's processor
-            if (p.ll_logits) {
-                cond = ll_wait1(p.ll_logits + (long long)b * V + v, p.ll_in_tag, p.ll_err);
-                unc = ll_wait1(p.ll_logits + (long long)(B + b) * V + v, p.ll_in_tag, p.ll_err);
-            } else {
-                cond = __ldcg(p.logits + (long long)b * p.logits_ld + v);
-                unc = __ldcg(p.logits + (long long)(B + b) * p.logits_ld + v);
-            }
+            float cond = __ldcg(p.logits + (long long)b * p.logits_ld + v);          // first half = "conditional" in HF's processor
+            float unc = __ldcg(p.logits + (long long)(B + b) * p.logits_ld + v);
             x = (suppress_eos && eos) ? -INFINITY : unc + (cond - unc) * c.cfg_scale;
         } else {
-            x = p.ll_logits ? ll_wait1(p.ll_logits + (long long)b * V + v, p.ll_in_tag, p.ll_err) : __ldcg(p.logits + (long long)b * p.logits_ld + v);
+            x = __ldcg(p.logits + (long long)b * p.logits_ld + v);
             if (suppress_eos && eos) x = -INFINITY;
         }
         s[v] = x;
+    }
     }
     // (2) MonotonicTimeShift, (3) TimeshiftBias, (4) temperature (decided on batch row 0)
     const int lts = p.last_ts[b];

@@ -35,12 +35,12 @@ constexpr int M2_PART = 66;                             // pairs per split parti
 
 struct __align__(16) M2Smem {
     float wbuf[2][MEGA_WBUF_FLOATS];
-    union {
+    union __align__(16) {
         float xs[M2_XS_FLOATS];
         SampleSmem sample;
-        struct { float sc[128]; float red[4][64]; float stat[2]; float qs[64]; } attn;
+        struct { __align__(16) float sc[128]; float red[4][64]; __align__(16) float qs[64]; float kns[64]; float vns[64]; float stat[2]; } attn;
     } u;
-    float xraw[M2_XRAW_FLOATS];                 // raw residual stream as of this CTA's last LayerNorm staging (residual source of its rows)
+    __align__(16) float xraw[M2_XRAW_FLOATS];   // raw residual stream as of this CTA's last LayerNorm staging (residual source of its rows)
     Mega2Phase phase[2];
     SampleParams sample_params;
     int ctrl[8];                                // cur_len, all_finished, error, prompt_len, encoder slots
@@ -157,14 +157,47 @@ __device__ __forceinline__ void m2_clear_ln_red(float* red, int tid) {
     if (tid < 32) red[tid] = 0.f;
 }
 
+// Every poll below puts ALL of a thread's loads in flight before it looks at the first tag (a wait per value would serialise one L2
+// round trip per value: measured +60 us / token).
+__device__ __forceinline__ bool ll_tag_ok4(ll_t a, ll_t b, ll_t c, ll_t d, unsigned tag) {
+    return (unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag && (unsigned)(c >> 32) == tag && (unsigned)(d >> 32) == tag;
+}
+__device__ __forceinline__ float ll_val(ll_t a) { return __uint_as_float((unsigned)a); }
+
 template <int NB>
 __device__ __forceinline__ void m2_stage_plain(const GemvParams& p, const ll_t* ll_in, unsigned tag, float* xs, int tid, int* err) {
     const int K4 = p.K >> 2;
-    for (int e = tid; e < NB * K4; e += M2_THREADS) {
-        const int bb = e / K4, c = e - bb * K4;
-        float4 v = make_float4(0, 0, 0, 0);
-        if (bb < p.B) v = ll_wait4(ll_in + (long long)bb * p.K + c * 4, tag, err);
-        reinterpret_cast<float4*>(xs)[e] = v;
+    constexpr int U = 3;                               // float4 per thread per batch (K = 3072: 1.5 per decoder row)
+    for (int e0 = tid; e0 < NB * K4; e0 += U * M2_THREADS) {
+        ll_t w[U][4];
+        bool on[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * M2_THREADS, bb = e / K4;
+            on[u] = e < NB * K4 && bb < p.B;
+        }
+        long long spin = 0;
+        while (true) {
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (on[u]) {
+                    const int e = e0 + u * M2_THREADS, bb = e / K4, c = e - bb * K4;
+                    const ll_t* src = ll_in + (long long)bb * p.K + c * 4;
+                    ll_load2(src, w[u][0], w[u][1]);
+                    ll_load2(src + 2, w[u][2], w[u][3]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (on[u]) ok = ok && ll_tag_ok4(w[u][0], w[u][1], w[u][2], w[u][3], tag);
+            if (ok || !ll_spin_check(spin, err)) break;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * M2_THREADS;
+            if (e < NB * K4) reinterpret_cast<float4*>(xs)[e] = on[u] ? make_float4(ll_val(w[u][0]), ll_val(w[u][1]), ll_val(w[u][2]), ll_val(w[u][3])) : make_float4(0, 0, 0, 0);
+        }
     }
 }
 
@@ -173,8 +206,8 @@ __device__ __forceinline__ void m2_stage_plain(const GemvParams& p, const ll_t* 
 // four PV accumulation chains — only the operand sources differ: q and the newest K/V row are polled from the exchange buffers, the
 // result leaves as tagged pairs (merged heads when one split covers the context, else a split partial that the split-0 CTA merges).
 __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const MegaLL& ll, bool is_self, int s, int h, int r, int slot, int L, int P,
-                                                  unsigned in_tag, unsigned out_tag, float* sc, float (*red)[64], float* stat, int tid,
-                                                  AttnRegs<M2_WARPS>& R, int* err) {
+                                                  unsigned in_tag, unsigned out_tag, float* sc, float (*red)[64], float* stat, float* qs, float* kns,
+                                                  float* vns, int tid, AttnRegs<M2_WARPS>& R, int* err) {
     constexpr int NW = M2_WARPS;
     constexpr int SC_ITERS = AttnRegs<NW>::SC_ITERS, PV_PRE = AttnRegs<NW>::PV_PRE;
     const int lane = tid & 31, warp = tid >> 5;
@@ -194,34 +227,40 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
     const int tok = (int)p.tok_stride;
     const float* vb = p.vc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
     const int sub = lane & 7, kq = lane >> 3;
-    // q: the only operand every lane needs from the previous phase
-    const float4 q0 = ll_wait4(ll.q + (long long)r * d + h * 64 + sub * 8, in_tag, err);
-    const float4 q1 = ll_wait4(ll.q + (long long)r * d + h * 64 + sub * 8 + 4, in_tag, err);
-    if (newest >= 0 && newest < nk) {                              // the appended key / value of this token arrive as tagged pairs
+    // q and (self-attention) the key / value row this token appended are polled ONCE per CTA — warp 14 takes q, warp 15 the new K | V
+    // row — into shared memory; everybody reads them from there after one CTA barrier.  (All 512 threads polling their own copy cost
+    // 16x the L2 polling traffic and, with the prefetched cache rows live in registers, pushed the kernel into spills.)
+    const bool has_new = newest >= 0 && newest < nk;
+    if (warp == NW - 2) {
+        const float2 v = ll_wait2(ll.q + (long long)r * d + h * 64 + lane * 2, in_tag, err);
+        qs[lane * 2] = v.x; qs[lane * 2 + 1] = v.y;
+    } else if (warp == NW - 1 && has_new) {
         const ll_t* kn = ll.kvnew + (long long)r * 2 * d + h * 64;
-        const ll_t* vn = kn + d;
-#pragma unroll
-        for (int it = 0; it < SC_ITERS; ++it) {
-            const int kk = it * 4 * NW + warp * 4 + kq;
-            if (kk == newest) { R.ka[it] = ll_wait4(kn + sub * 8, in_tag, err); R.kb4[it] = ll_wait4(kn + sub * 8 + 4, in_tag, err); R.kvalid[it] = 1; }
+        ll_t w[4];
+        long long spin = 0;
+        while (true) {
+            ll_load2(kn + lane * 2, w[0], w[1]);
+            ll_load2(kn + d + lane * 2, w[2], w[3]);
+            if (ll_tag_ok4(w[0], w[1], w[2], w[3], in_tag) || !ll_spin_check(spin, err)) break;
         }
-        if (warp < 4) {
-#pragma unroll
-            for (int i = 0; i < PV_PRE; ++i)
-                if (warp + 4 * i == newest) R.vpre[i] = ll_wait2(vn + lane * 2, in_tag, err);
-        }
+        kns[lane * 2] = ll_val(w[0]); kns[lane * 2 + 1] = ll_val(w[1]);
+        vns[lane * 2] = ll_val(w[2]); vns[lane * 2 + 1] = ll_val(w[3]);
     }
+    __syncthreads();
+    const float4 q0 = *reinterpret_cast<const float4*>(qs + sub * 8), q1 = *reinterpret_cast<const float4*>(qs + sub * 8 + 4);
 #pragma unroll
     for (int it = 0; it < SC_ITERS; ++it) {
         const int kk = it * 4 * NW + warp * 4 + kq;
-        const float4 a = R.ka[it], b = R.kb4[it];
+        const bool is_new = kk == newest;
+        const float4 a = is_new ? *reinterpret_cast<const float4*>(kns + sub * 8) : R.ka[it];
+        const float4 b = is_new ? *reinterpret_cast<const float4*>(kns + sub * 8 + 4) : R.kb4[it];
         float dd = q0.x * a.x;
         dd = fmaf(q0.y, a.y, dd); dd = fmaf(q0.z, a.z, dd); dd = fmaf(q0.w, a.w, dd);
         dd = fmaf(q1.x, b.x, dd); dd = fmaf(q1.y, b.y, dd); dd = fmaf(q1.z, b.z, dd); dd = fmaf(q1.w, b.w, dd);
         dd += __shfl_xor_sync(0xffffffffu, dd, 1);
         dd += __shfl_xor_sync(0xffffffffu, dd, 2);
         dd += __shfl_xor_sync(0xffffffffu, dd, 4);
-        if (kk < nk && sub == 0) sc[kk] = R.kvalid[it] ? dd : -INFINITY;
+        if (kk < nk && sub == 0) sc[kk] = (R.kvalid[it] || is_new) ? dd : -INFINITY;
     }
     __syncthreads();
     if (warp < 4) {
@@ -248,9 +287,10 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
         for (int i = 0; i < PV_PRE; ++i) {
             const int kk = warp + 4 * i;
             const float pk = __shfl_sync(0xffffffffu, pv[i >> 3], kk & 31);
+            const float2 vv = kk == newest ? *reinterpret_cast<const float2*>(vns + lane * 2) : R.vpre[i];
             if (kk < nk) {
-                o.x = fmaf(pk, R.vpre[i].x, o.x);
-                o.y = fmaf(pk, R.vpre[i].y, o.y);
+                o.x = fmaf(pk, vv.x, o.x);
+                o.y = fmaf(pk, vv.y, o.y);
             }
         }
         if (nk > 64) {
@@ -261,7 +301,7 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
                 for (int i = 0; i < 8; ++i) {
                     const int kk = 32 * t + warp + 4 * i;
                     vv[i] = make_float2(0.f, 0.f);
-                    if (kk < nk) vv[i] = kk == newest ? ll_wait2(ll.kvnew + (long long)r * 2 * d + d + h * 64 + lane * 2, in_tag, err) : ldcg2(vb + kk * tok + lane * 2);
+                    if (kk < nk) vv[i] = kk == newest ? *reinterpret_cast<const float2*>(vns + lane * 2) : ldcg2(vb + kk * tok + lane * 2);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -293,41 +333,61 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
 
 // merge of the S split partials of (row r, head h) by the CTA that computed split 0: splits visited in index order,
 // out = sum_s w_s o_s / sum_s w_s l_s with w_s = exp(m_s - max m) — decode_attention_merge's arithmetic, operands polled
-__device__ __forceinline__ void m2_attention_merge(const DecAttnParams& p, const MegaLL& ll, int h, int r, unsigned tag, int tid, int* err) {
-    if (tid >= 64) return;
+__device__ __forceinline__ void m2_attention_merge(const DecAttnParams& p, const MegaLL& ll, int h, int r, unsigned tag, float* msh /* >= 2 * 32 floats of shared memory */,
+                                                   int tid, int* err) {
+    // called by the WHOLE CTA (uniform).  Threads 64 .. 64+S-1 poll the (m, l) pair of one split each into shared memory, threads 0..63
+    // poll their output dim of every split (S <= 8: one batch; beyond that: rolled), then 64 threads combine.
     const int S = p.n_splits, d = p.H * 64;
     const ll_t* base = ll.part + ((long long)r * p.H + h) * ll.max_splits * M2_PART;
-    float num = 0.f, den = 0.f;
-    if (S <= 8) {
-        float2 mv[8]; float ov[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            mv[s] = make_float2(-INFINITY, 0.f); ov[s] = 0.f;
-            if (s < S) { mv[s] = ll_wait2(base + (long long)s * M2_PART + 64, tag, err); ov[s] = ll_wait1(base + (long long)s * M2_PART + tid, tag, err); }
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + (tid - 64);
+        if (tid >= 64 && tid < 96 && s < S) {
+            const float2 mv = ll_wait2(base + (long long)s * M2_PART + 64, tag, err);
+            if (s < 32) { msh[s] = mv.x; msh[32 + s] = mv.y; }
         }
-        float mmax = -INFINITY;
+    }
+    float ov[8];
+    if (tid < 64 && S <= 8) {
+        ll_t oo[8];
+        long long spin = 0;
+        while (true) {
+            bool ok = true;
 #pragma unroll
-        for (int s = 0; s < 8; ++s) if (s < S) mmax = fmaxf(mmax, mv[s].x);
+            for (int s = 0; s < 8; ++s)
+                if (s < S) asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(oo[s]) : "l"(base + (long long)s * M2_PART + tid) : "memory");
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (s < S) ok = ok && (unsigned)(oo[s] >> 32) == tag;
+            if (ok || !ll_spin_check(spin, err)) break;
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) ov[s] = s < S ? ll_val(oo[s]) : 0.f;
+    }
+    __syncthreads();
+    if (tid >= 64) return;
+    float num = 0.f, den = 0.f;
+    float mmax = -INFINITY;
+    if (S <= 8) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s) if (s < S) mmax = fmaxf(mmax, msh[s]);
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            if (s < S && mv[s].y > 0.f) {
-                const float w = expf(mv[s].x - mmax);
+            if (s < S && msh[32 + s] > 0.f) {
+                const float w = expf(msh[s] - mmax);
                 num = fmaf(w, ov[s], num);
-                den = fmaf(w, mv[s].y, den);
+                den = fmaf(w, msh[32 + s], den);
             }
         }
     } else {
-        float mmax = -INFINITY;
 #pragma unroll 1
-        for (int s = 0; s < S; ++s) mmax = fmaxf(mmax, ll_wait2(base + (long long)s * M2_PART + 64, tag, err).x);
+        for (int s = 0; s < S; ++s) mmax = fmaxf(mmax, msh[s]);
 #pragma unroll 1
         for (int s = 0; s < S; ++s) {
-            const float2 mv = ll_wait2(base + (long long)s * M2_PART + 64, tag, err);
-            const float ov = ll_wait1(base + (long long)s * M2_PART + tid, tag, err);
-            if (mv.y > 0.f) {
-                const float w = expf(mv.x - mmax);
-                num = fmaf(w, ov, num);
-                den = fmaf(w, mv.y, den);
+            const float o1 = ll_wait1(base + (long long)s * M2_PART + tid, tag, err);
+            if (msh[32 + s] > 0.f) {
+                const float w = expf(msh[s] - mmax);
+                num = fmaf(w, o1, num);
+                den = fmaf(w, msh[32 + s], den);
             }
         }
     }
@@ -431,15 +491,17 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
                         if (g.bias) v += bias_v;
                         v = apply_act(v, sg.act) * sg.alpha;
                         if (ph2.res_xraw) v += sm.xraw[lane * d + n];
-                        if (ph2.plain_out[si]) {
-                            sg.out[(long long)lane * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin)] = v;
-                            __threadfence();      // K/V cache rows are read by later tokens through plain loads: order them before this thread's next tagged store
-                        }
-                        if (osel != LL_NONE) {
+                        if (osel != LL_NONE) {         // the tagged copy first: it is what this token's next phase waits for
                             ll_t* out = ll_buf(mp.ll, osel);
                             const long long width = osel == LL_K || osel == LL_V ? 2 * d : (osel == LL_H ? g.N : (osel == LL_LOGITS ? mp.V : d));
                             const int col = osel == LL_V ? d + (n - sg.n_begin) : (n - sg.n_begin);
                             ll_store(out + (long long)lane * width + col, v, out_tag);
+                        }
+                        if (ph2.plain_out[si]) {
+                            sg.out[(long long)lane * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin)] = v;
+                            // K/V cache rows are read by LATER tokens through plain loads: order them before this thread's next tagged
+                            // store (the one of the following phase; this token's were issued above)
+                            __threadfence();
                         }
                     }
                 }
@@ -457,8 +519,9 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
                     const int slot = a.row_slot ? sm.ctrl[4 + r] : r;
                     // K/V of the cache first (they do not depend on this token's phases), q and the appended row are polled inside
                     decode_attention_load<M2_WARPS>(a, s, h, r, slot, L, P, tid, areg);
-                    m2_attention_unit(a, mp.ll, is_self, s, h, r, slot, L, P, in_tag, out_tag, sm.u.attn.sc, sm.u.attn.red, sm.u.attn.stat, tid, areg, err);
-                    if (a.n_splits > 1 && s == 0) m2_attention_merge(a, mp.ll, h, r, out_tag, tid, err);
+                    m2_attention_unit(a, mp.ll, is_self, s, h, r, slot, L, P, in_tag, out_tag, sm.u.attn.sc, sm.u.attn.red, sm.u.attn.stat, sm.u.attn.qs,
+                                      sm.u.attn.kns, sm.u.attn.vns, tid, areg, err);
+                    if (a.n_splits > 1 && s == 0) { __syncthreads(); m2_attention_merge(a, mp.ll, h, r, out_tag, sm.u.attn.sc, tid, err); }
                     __syncthreads();
                 }
             } else {

@@ -70,6 +70,25 @@ class SongDecoder:
         return streams
 
 
+    def decode_songs(self, n_songs: int, n_windows: int, prompt_fn: Callable[[int, int, List[List[int]]], List[int]],
+                     generate_kwargs_fn: Callable[[int], dict], windows_per_song: Optional[int] = None) -> List[List[List[int]]]:
+        """`n_songs` songs of equal window count decoded in LOCK-STEP (BASELINE configs[3]: 8 songs per GPU): window i of every
+        song is one batch-`n_songs` `generate()` call over the resident encoder slots (song s, window i at slot
+        s * windows_per_song + i).  `prompt_fn(s, i, streams_of_song_s)` must return prompts of equal length across songs.
+        Returns streams[s][i]."""
+        stride = windows_per_song or n_windows
+        streams: List[List[List[int]]] = [[] for _ in range(n_songs)]
+        for i in range(n_windows):
+            prompts = [prompt_fn(s, i, streams[s]) for s in range(n_songs)]
+            assert len({len(p) for p in prompts}) == 1, "lock-step batch needs equal prompt lengths (pad on the left otherwise)"
+            prompt = torch.tensor(prompts, dtype=torch.long)
+            ids = self.engine.generate([s * stride + i for s in range(n_songs)], prompt, prompt.ne(self.layout.pad_id), self.layout,
+                                       generate_kwargs_fn(i), position_rule=self.model.position_rule)
+            for s in range(n_songs):
+                streams[s].append(ids[s, prompt.shape[1]:].tolist())
+        return streams
+
+
 def shard_songs(lengths: Sequence[float], world_size: int) -> List[List[int]]:
     """Songs sorted by length (longest first), dealt round-robin: rank r gets shard[r] (indices into `lengths`)."""
     order = sorted(range(len(lengths)), key=lambda i: (-lengths[i], i))

@@ -58,3 +58,19 @@ def patch_whisper_config(d_model=768, layers=12, heads=12, ffn=3072):
                    encoder_ffn_dim=ffn, decoder_ffn_dim=ffn)
 
     WhisperConfig.from_pretrained = classmethod(_fp)
+
+
+def reference_slider_path():
+    """The reference's `SliderPath` class, loaded from its two numpy-only source files (slider_path.py, path_approximator.py)
+    without importing the rest of the `osuT5.osuT5.inference` package."""
+    import importlib.util
+    base = os.path.join(REFERENCE_ROOT, "osuT5", "osuT5", "inference")
+    pkg = types.ModuleType("_ref_inference")
+    pkg.__path__ = [base]
+    sys.modules["_ref_inference"] = pkg
+    for name in ("path_approximator", "slider_path"):
+        spec = importlib.util.spec_from_file_location(f"_ref_inference.{name}", os.path.join(base, f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"_ref_inference.{name}"] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules["_ref_inference.slider_path"].SliderPath

@@ -158,8 +158,14 @@ def test_sampling_chain_keep_set_matches_oracle(tiny, layout, top_k, top_p, B):
         got, chosen = model.engine.logits_chain(lg.cuda(), ids, P, layout, gk, step=step, has_last_scores=step > 0)
         got = got.cpu()
         keep_w, keep_g = want != float("-inf"), got != float("-inf")
-        assert torch.equal(keep_w, keep_g), f"step {step}: keep-sets differ at {(keep_w != keep_g).nonzero()[:5].tolist()} (|want|={int(keep_w.sum())}, |got|={int(keep_g.sum())})"
         pw, pg = torch.softmax(want, -1), torch.softmax(got, -1)
+        # Exact keep-set, except ids whose probability is below 1e-9 on BOTH sides: LookbackBias writes log(clip((s - 1) P_eos / P_ev, 0, 1))
+        # at the first time-shift id, and with a peaked distribution s - 1 is a one-ulp quantity (6e-8 or exactly 0), so that id sits at
+        # probability 5e-12 or -inf depending on the last rounding; it can never be drawn either way.
+        relevant = (pw > 1e-9) | (pg > 1e-9)
+        bad = (keep_w != keep_g) & relevant
+        assert not bad.any(), f"step {step}: keep-sets differ at {bad.nonzero()[:5].tolist()} (|want|={int(keep_w.sum())}, |got|={int(keep_g.sum())})"
+        assert int((keep_w != keep_g).sum()) <= B, "more than one knife-edge id per row"
         assert (pw - pg).abs().max() <= 1e-6, (pw - pg).abs().max()
         for b in range(B):
             assert keep_w[b, int(chosen[b])], f"step {step} row {b}: drew id {int(chosen[b])} outside the keep-set"
