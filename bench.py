@@ -299,6 +299,10 @@ def main() -> None:
     if args.pdl:
         model.engine.set_option("pdl", 1)
     model.engine.set_option("mega", args.mega)
+    if os.environ.get("MB200_LL_REPS"):
+        model.engine.set_option("ll_reps", int(os.environ["MB200_LL_REPS"]))
+    if os.environ.get("MB200_LL_SLEEP"):
+        model.engine.set_option("ll_sleep", int(os.environ["MB200_LL_SLEEP"]))
     song = SongDecoder(model, layout)
     all_windows = torch.stack(songs)                                   # (S, n_windows, samples)
     pinned = all_windows.pin_memory()

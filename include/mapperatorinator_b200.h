@@ -150,6 +150,16 @@ int mb200_dit_sample_loop(mb200_dit* d, const float* z, const float* c, const fl
                           float cfg_scale, const mb200_dit_mask* mask, const float* schedule, int32_t steps, const float* noise,
                           float* out, void* cuda_stream);
 
+/* Slider end-point recompute of the denoised_fn closure (diffusion_pipeline.py:203-222: SliderPath(curve_type, control points)
+ * .position_at(length / max_length), osuT5/osuT5/inference/slider_path.py:57-99, path_approximator.py:12-253) on the device.
+ * mb200_dit_set_sliders registers the sliders of the chunk about to be sampled (HOST arrays, chunk-relative sequence indices; n = 0
+ * clears): cp_offsets [n+1] prefix offsets into cp_index, end_index [n], type [n] (0 Bezier, 1 PerfectCurve, 2 Catmull, 3 Linear),
+ * length [n] in osu! pixels.  The next mb200_dit_sample_loop then applies the recompute to the start state and to every step's
+ * predicted x_start, inside the loop.  mb200_dit_apply_sliders runs the recompute once on x (DEVICE [N, 2, T], in place). */
+int mb200_dit_set_sliders(mb200_dit* d, int32_t n, const int32_t* cp_offsets, const int32_t* cp_index, const int32_t* end_index,
+                          const int32_t* type, const float* length);
+int mb200_dit_apply_sliders(mb200_dit* d, float* x, int32_t N, int32_t T, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Measurement / tuning hooks used by bench.py (not part of the reference-facing boundary).
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -52,7 +52,7 @@ ABI_SYMBOLS = [
     "mb200_model_create", "mb200_model_destroy", "mb200_model_set_weight", "mb200_model_finalize", "mb200_model_encode",
     "mb200_model_generate", "mb200_model_forward_logits",
     "mb200_dit_create", "mb200_dit_destroy", "mb200_dit_set_weight", "mb200_dit_finalize", "mb200_dit_forward_with_cfg",
-    "mb200_dit_sample_loop", "mb200_dit_set_option",
+    "mb200_dit_sample_loop", "mb200_dit_set_option", "mb200_dit_set_sliders", "mb200_dit_apply_sliders",
     "mb200_launch_count", "mb200_model_set_option", "mb200_model_profile_step", "mb200_model_read_trace", "mb200_model_mega_stats", "mb200_model_logits_chain",
     "mb200_op_gemm", "mb200_op_gemm_tc", "mb200_set_tensor_cores", "mb200_op_layernorm", "mb200_op_attention",
 ]
@@ -95,6 +95,8 @@ def load() -> C.CDLL:
     lib.mb200_dit_sample_loop.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, C.POINTER(DitMaskC), vp, i32, vp, vp, vp]
     lib.mb200_model_logits_chain.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, C.POINTER(GenerateParamsC), i32, i32, vp, vp, vp]
     lib.mb200_dit_set_option.argtypes = [vp, C.c_char_p, i32]
+    lib.mb200_dit_set_sliders.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.mb200_dit_apply_sliders.argtypes = [vp, vp, i32, i32, vp]
     lib.mb200_op_gemm.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, f32, vp, i64, vp, i64, i32, i32, i32, i32, vp]
     lib.mb200_op_gemm_tc.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, f32, vp, i64, i32, i32, i32, vp]
     lib.mb200_set_tensor_cores.argtypes = [i32]

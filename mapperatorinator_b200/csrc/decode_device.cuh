@@ -25,10 +25,12 @@ __device__ __forceinline__ void ll_store2(ll_t* p, float a, float b, unsigned ta
 __device__ __forceinline__ void ll_load2(const ll_t* p, ll_t& a, ll_t& b) {                // p 16-byte aligned
     asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
+static __constant__ int c_ll_sleep_ns = 0;      // tuning knob (engine option "ll_sleep"): back off this long after a failed poll (0 = spin)
 constexpr long long LL_SPIN_LIMIT = 1ll << 24;      // ~ seconds; a dataflow wait that long is a bug, never a slow producer
 // Wait for one / two / four consecutive pairs carrying `tag`.  Bounded: on a timeout (or when another CTA raised `err`) the error flag is
 // set and zeros are returned, so a logic error ends the launch instead of hanging the GPU.
 __device__ __forceinline__ bool ll_spin_check(long long& spin, int* err) {
+    if (c_ll_sleep_ns > 0) __nanosleep((unsigned)c_ll_sleep_ns);
     if ((++spin & 0x3FF) == 0 && (spin > LL_SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0)) { atomicCAS(err, 0, 4); return false; }
     return true;
 }
@@ -934,9 +936,11 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
             const float4 o = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
             xo[i] = o;
             if (p.ll_x_out) {
-                ll_t* lo = p.ll_x_out + (long long)row * p.d_model + i * 4;
-                ll_store2(lo, o.x, o.y, p.ll_out_tag);
-                ll_store2(lo + 2, o.z, o.w, p.ll_out_tag);
+                for (int rep = 0; rep < p.ll_reps; ++rep) {
+                    ll_t* lo = p.ll_x_out + rep * p.ll_x_rep + (long long)row * p.d_model + i * 4;
+                    ll_store2(lo, o.x, o.y, p.ll_out_tag);
+                    ll_store2(lo + 2, o.z, o.w, p.ll_out_tag);
+                }
             }
         }
     }

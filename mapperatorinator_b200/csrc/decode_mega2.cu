@@ -218,7 +218,7 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
     ll_t* part = ll.part + (((long long)r * p.H + h) * ll.max_splits + s) * M2_PART;
     ll_t* att = ll.att + (long long)r * d + h * 64;
     if (nk <= 0) {                                                 // empty split (uniform across the CTA)
-        if (p.n_splits == 1) { if (tid < 64) ll_store(att + tid, 0.f, out_tag); return; }
+        if (p.n_splits == 1) { if (tid < 64) for (int rep = 0; rep < ll.reps; ++rep) ll_store(att + rep * ll.x_rep + tid, 0.f, out_tag); return; }
         if (tid < 64) ll_store(part + tid, 0.f, out_tag);
         if (tid == 0) { ll_store(part + 64, -INFINITY, out_tag); ll_store(part + 65, 0.f, out_tag); }
         stat[0] = -INFINITY; stat[1] = 0.f;
@@ -323,7 +323,8 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
         if (p.n_splits == 1) {
             // one split holds the whole context: the merge degenerates to o / l (w = exp(m - m) = 1: the same bits as the general path)
             const float num = fmaf(1.f, v, 0.f), den = fmaf(1.f, stat[1], 0.f);
-            ll_store(att + tid, (stat[1] > 0.f && den > 0.f) ? num / den : 0.f, out_tag);
+            const float o = (stat[1] > 0.f && den > 0.f) ? num / den : 0.f;
+            for (int rep = 0; rep < ll.reps; ++rep) ll_store(att + rep * ll.x_rep + tid, o, out_tag);
         } else {
             ll_store(part + tid, v, out_tag);
             if (tid == 0) { ll_store(part + 64, stat[0], out_tag); ll_store(part + 65, stat[1], out_tag); }
@@ -391,10 +392,13 @@ __device__ __forceinline__ void m2_attention_merge(const DecAttnParams& p, const
             }
         }
     }
-    ll_store(ll.att + (long long)r * d + h * 64 + tid, den > 0.f ? num / den : 0.f, tag);
+    const float o = den > 0.f ? num / den : 0.f;
+    for (int rep = 0; rep < ll.reps; ++rep) ll_store(ll.att + rep * ll.x_rep + (long long)r * d + h * 64 + tid, o, tag);
 }
 
-template <int NB>
+// TRACE = true is a separate instantiation for tools/mega2_trace.py: CTAs 0, 1, 100 and 140 stamp clock64 at four points of every phase
+// of token `trace_step` (phase start, input staged, weights landed, rows / units done); the production kernel carries no stamp code.
+template <int NB, bool TRACE>
 __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Params mp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     M2Smem& sm = *reinterpret_cast<M2Smem*>(smem_raw);
@@ -420,7 +424,8 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
     // under the tag the first phase of step 0 expects: "last phase of step -1"
     if (cta == 0) {
         const unsigned t0 = ll_tag(-1, mp.n_phases - 1);
-        for (int i = tid; i < mp.rows * d; i += M2_THREADS) ll_store(mp.ll.x + i, mp.x_in[i], t0);
+        for (int rep = 0; rep < mp.ll.reps; ++rep)
+            for (int i = tid; i < mp.rows * d; i += M2_THREADS) ll_store(mp.ll.x + rep * mp.ll.x_rep + i, mp.x_in[i], t0);
         if (tid == 0) {
             ll_store(mp.ll.hdr + 0, __int_as_float(ld_state(&mp.st->cur_len)), t0);
             ll_store(mp.ll.hdr + 1, __int_as_float(ld_state(&mp.st->all_finished)), t0);
@@ -447,7 +452,11 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
         __syncthreads();
         const int cur_pos = sm.ctrl[0] - 1, fin = sm.ctrl[1], e = sm.ctrl[2], P = sm.ctrl[3];
         if (fin || e) break;
+        const int tslot = cta == 0 ? 0 : (cta == 1 ? 1 : (cta == 100 ? 2 : (cta == 140 ? 3 : -1)));
+        const bool tracing = TRACE && mp.trace != nullptr && step == mp.trace_step && tslot >= 0 && tid == 0;
+#define M2_TRACE(slot) do { if (tracing) mp.trace[((long long)tslot * mp.n_phases + pi) * 4 + (slot)] = (unsigned long long)clock64(); } while (0)
         for (int pi = 0; pi < mp.n_phases; ++pi) {
+            M2_TRACE(0);
             const Mega2Phase& ph2 = sm.phase[cur];
             const MegaPhase& ph = ph2.base;
             const unsigned in_tag = pi == 0 ? ll_tag(step - 1, mp.n_phases - 1) : ll_tag(step, pi - 1);
@@ -470,14 +479,16 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
                     if (n < r1 && g.bias) bias_pref = __ldg(g.bias + n);
                 }
                 if (r0 < r1) {
-                    const ll_t* in = ll_buf(mp.ll, ph2.in_sel);
+                    const ll_t* in = ll_buf(mp.ll, ph2.in_sel) + (cta % mp.ll.reps) * (ph2.in_sel == LL_H ? mp.ll.h_rep : mp.ll.x_rep);
                     if (g.xmode == X_LAYERNORM) m2_stage_ln<NB>(g, in, in_tag, sm.u.xs, sm.xraw, sm.ln_red, tid, err);
                     else m2_stage_plain<NB>(g, in, in_tag, sm.u.xs, tid, err);
                 }
                 __syncthreads();
+                M2_TRACE(1);
                 // the next GEMV's weight slice is requested only now (after this phase's small latency-critical loads), by the last warp
                 if (tid == M2_THREADS - 32) prefetch_weights(ph.nx_W, ph.nx_ldw, ph.nx_N, ph.nx_K, sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, ph.nx_rpc);
                 wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err);
+                M2_TRACE(2);
                 int j = 0;
 #pragma unroll 1
                 for (int n = r0 + warp; n < r1; n += M2_WARPS, ++j) {
@@ -486,14 +497,25 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
                     const GemvSeg& sg = g.seg[si];
                     const int osel = ph2.out_sel[si];
                     const float mine = gemv_dot<NB, false>(g.K, sm.wbuf[buf] + (long long)(n - r0) * g.K, sm.u.xs, lane);
+                    float v = 0.f;
                     if (lane < NB && lane < g.B) {
-                        float v = mine;
+                        v = mine;
                         if (g.bias) v += bias_v;
                         v = apply_act(v, sg.act) * sg.alpha;
                         if (ph2.res_xraw) v += sm.xraw[lane * d + n];
+                    }
+                    if (osel == LL_X || osel == LL_H) {
+                        // replicated buffers: lane l stores replica l / NB of decoder row l % NB (the value comes from lane l % NB)
+                        const int b = lane % NB, rep = lane / NB;
+                        const float vb = __shfl_sync(0xffffffffu, v, b);
+                        if (rep < mp.ll.reps && b < g.B) {
+                            const long long width = osel == LL_H ? g.N : d;
+                            ll_store(ll_buf(mp.ll, osel) + rep * (osel == LL_H ? mp.ll.h_rep : mp.ll.x_rep) + (long long)b * width + (n - sg.n_begin), vb, out_tag);
+                        }
+                    } else if (lane < NB && lane < g.B) {
                         if (osel != LL_NONE) {         // the tagged copy first: it is what this token's next phase waits for
                             ll_t* out = ll_buf(mp.ll, osel);
-                            const long long width = osel == LL_K || osel == LL_V ? 2 * d : (osel == LL_H ? g.N : (osel == LL_LOGITS ? mp.V : d));
+                            const long long width = osel == LL_K || osel == LL_V ? 2 * d : (osel == LL_LOGITS ? mp.V : d);
                             const int col = osel == LL_V ? d + (n - sg.n_begin) : (n - sg.n_begin);
                             ll_store(out + (long long)lane * width + col, v, out_tag);
                         }
@@ -533,9 +555,11 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();                              // xs / attention scratch free for the next phase; the next descriptor has landed
+            M2_TRACE(3);
             cur ^= 1;
         }
     }
+#undef M2_TRACE
     // drain the weight prefetch that is still in flight so no bulk copy outlives the CTA
     wait_weights(&sm.mbar[g_idx & 1], (g_idx >> 1) & 1, err);
 }
@@ -544,13 +568,20 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
 
 size_t mega2_smem_bytes() { return sizeof(M2Smem) + 128; }
 
+int mega2_set_poll_sleep(int ns) {
+    MB_CUDA_CHECK(cudaMemcpyToSymbol(c_ll_sleep_ns, &ns, sizeof(int)));
+    return 0;
+}
+
 int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
-        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
+        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
         int per_sm = 0;
-        MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel_ll<2>, M2_THREADS, mega2_smem_bytes()));
+        MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel_ll<2, true>, M2_THREADS, mega2_smem_bytes()));
         MB_REQUIRE(per_sm >= 1, "dataflow megakernel does not fit on an SM");
         configured = true;
     }
@@ -559,7 +590,8 @@ int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream) {
     MB_REQUIRE(mp.d_model <= 1024, "residual scratch holds d_model <= 1024");
     Mega2Params p = mp;
     void* args[] = {&p};
-    const void* fn = mp.rows == 1 ? (const void*)decode_megakernel_ll<1> : (const void*)decode_megakernel_ll<2>;
+    const void* fn = mp.trace ? (mp.rows == 1 ? (const void*)decode_megakernel_ll<1, true> : (const void*)decode_megakernel_ll<2, true>)
+                              : (mp.rows == 1 ? (const void*)decode_megakernel_ll<1, false> : (const void*)decode_megakernel_ll<2, false>);
     // Cooperative launch for its co-residency guarantee: every CTA polls values that other CTAs produce, so all of them must be resident.
     MB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(M2_THREADS), args, mega2_smem_bytes(), stream));
     ++g_launch_count;

@@ -138,6 +138,40 @@ __global__ void dit_update_kernel(const float* __restrict__ o4, float* __restric
     x[idx] = mean + sc.nonzero * expf(0.5f * logvar) * noise[(long long)k * N * 2 * T + idx];
 }
 
+// The same update in two halves around the slider recompute (denoised_fn with sliders, diffusion_pipeline.py:203-222):
+//   (a) x0 = predicted x_start after the in-paint mask, for every (n, ch, t);
+//   [slider.cu: conditional half -> pixels, slider ends recomputed, pixels written back to both halves of x0]
+//   (b) clamp, posterior mean, noise.
+__global__ void dit_x0_kernel(const float* __restrict__ o4, const float* __restrict__ x, const float* __restrict__ z,
+                              const unsigned char* __restrict__ inpaint, int N, int T, float cfg_scale, const StepConst* __restrict__ sched,
+                              const int* __restrict__ step_ptr, float* __restrict__ x0buf) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * 2 * T) return;
+    const StepConst sc = sched[*step_ptr];
+    const int n = idx / (2 * T), rem = idx - n * 2 * T, ch = rem / T, t = rem - ch * T, half_n = N / 2;
+    const float cond = o4[((long long)(n % half_n) * T + t) * 4 + ch];
+    const float unc = o4[((long long)(half_n + n % half_n) * T + t) * 4 + ch];
+    const float eps = unc + cfg_scale * (cond - unc);
+    float x0 = sc.sqrt_recip * x[idx] - sc.sqrt_recipm1 * eps;
+    if (inpaint && !inpaint[idx]) x0 = z[idx];
+    x0buf[idx] = x0;
+}
+__global__ void dit_finish_kernel(const float* __restrict__ o4, float* __restrict__ x, const float* __restrict__ x0buf, const float* __restrict__ noise,
+                                  int N, int T, const StepConst* __restrict__ sched, const int* __restrict__ step_ptr) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * 2 * T) return;
+    const int k = *step_ptr;
+    const StepConst sc = sched[k];
+    const int n = idx / (2 * T), rem = idx - n * 2 * T, ch = rem / T, t = rem - ch * T;
+    const float v = o4[((long long)n * T + t) * 4 + 2 + ch];
+    const float frac = (v + 1.0f) / 2.0f;
+    const float logvar = frac * sc.max_log + (1.0f - frac) * sc.min_log;
+    const float xt = x[idx];
+    const float x0 = fminf(fmaxf(x0buf[idx], -2.0f), 2.0f);
+    const float mean = sc.coef1 * x0 + sc.coef2 * xt;
+    x[idx] = mean + sc.nonzero * expf(0.5f * logvar) * noise[(long long)k * N * 2 * T + idx];
+}
+
 __global__ void dit_step_advance_kernel(int* step_ptr) { *step_ptr += 1; }
 
 struct BlockW { const float *in_w, *in_b, *out_w, *out_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *ada_w, *ada_b; };
@@ -159,6 +193,9 @@ struct mb200_dit {
     // caller pointer
     DevBufD state, z_in, c_in, y_in, noise_in, inpaint_in, dense_in, sched, step_ctr, mods_cur, fmod_cur;
     std::map<std::tuple<int, int, int, int, int>, std::pair<cudaGraphExec_t, long long>> step_graphs;   // (N, T, mask mode, band, in-paint) -> graph, nodes
+    // sliders of the current chunk (mb200_dit_set_sliders); the step graph is keyed by their presence, the arrays live in fixed buffers
+    DevBufD sl_off, sl_idx, sl_end, sl_type, sl_len, sl_pix, sl_err, x0buf;
+    int n_sliders = 0, sl_cap = 0, sl_cp_cap = 0;
     cudaStream_t cap_stream = nullptr;
     bool use_graph = true;
     float graph_cfg_scale = 0.f; const void* graph_noise = nullptr; const void* graph_mods = nullptr;   // what the cached graphs baked
@@ -445,15 +482,37 @@ extern "C" int mb200_dit_sample_loop(mb200_dit* d, const float* z, const float* 
     int* step_ptr = reinterpret_cast<int*>(d->step_ctr.p);
     const unsigned char* ip = inpaint ? reinterpret_cast<const unsigned char*>(d->inpaint_in.p) : nullptr;
     const int n_mods = (cf.depth * N * 6 + N * 2) * (dm / 4);
+    SliderSet sl{};
+    sl.n = d->n_sliders;
+    if (sl.n > 0) {
+        sl.cp_offsets = reinterpret_cast<const int*>(d->sl_off.p); sl.cp_index = reinterpret_cast<const int*>(d->sl_idx.p);
+        sl.end_index = reinterpret_cast<const int*>(d->sl_end.p); sl.type = reinterpret_cast<const int*>(d->sl_type.p); sl.length = d->sl_len.f();
+        MB_TRY(d->x0buf.ensure(maxR * 2 * 4)); MB_TRY(d->sl_pix.ensure((size_t)2 * cf.max_seq_len * 4));
+        // the start state itself goes through the closure first (diffusion_pipeline.py:233: z_part = denoised_fn(z_part)); the in-paint
+        // source of every later step is that corrected state (the closure reads the re-bound z_part)
+        MB_TRY(launch_slider_recompute(sl, d->state.f(), N, T, d->sl_pix.f(), reinterpret_cast<int*>(d->sl_err.p), st));
+        MB_CUDA_CHECK(cudaMemcpyAsync(d->z_in.p, d->state.p, state_bytes, cudaMemcpyDeviceToDevice, st));
+    }
     auto one_step = [&](cudaStream_t s) -> int {
         dit_gather_mods_kernel<<<std::min(296, (n_mods + 255) / 256), 256, 0, s>>>(
             reinterpret_cast<const float4*>(d->mods.p), reinterpret_cast<const float4*>(d->fmod.p), step_ptr, cf.depth, steps, N, dm / 4,
             reinterpret_cast<float4*>(d->mods_cur.p), reinterpret_cast<float4*>(d->fmod_cur.p));
         MB_LAUNCH_CHECK();
         MB_TRY(dit_forward(d, d->state.f(), d->c_in.f(), N, T, d->mods_cur.f(), d->fmod_cur.f(), &mk, s));
-        dit_update_kernel<<<((int)total + 255) / 256, 256, 0, s>>>(d->o4.f(), d->state.f(), d->z_in.f(), ip, d->noise_in.f(), N, T, cfg_scale,
-                                                                  reinterpret_cast<const StepConst*>(d->sched.p), step_ptr);
-        MB_LAUNCH_CHECK();
+        if (sl.n > 0) {
+            dit_x0_kernel<<<((int)total + 255) / 256, 256, 0, s>>>(d->o4.f(), d->state.f(), d->z_in.f(), ip, N, T, cfg_scale,
+                                                                  reinterpret_cast<const StepConst*>(d->sched.p), step_ptr, d->x0buf.f());
+            MB_LAUNCH_CHECK();
+            MB_TRY(launch_slider_recompute(sl, d->x0buf.f(), N, T, d->sl_pix.f(), reinterpret_cast<int*>(d->sl_err.p), s));
+            dit_finish_kernel<<<((int)total + 255) / 256, 256, 0, s>>>(d->o4.f(), d->state.f(), d->x0buf.f(), d->noise_in.f(), N, T,
+                                                                      reinterpret_cast<const StepConst*>(d->sched.p), step_ptr);
+            MB_LAUNCH_CHECK();
+            ++g_launch_count;
+        } else {
+            dit_update_kernel<<<((int)total + 255) / 256, 256, 0, s>>>(d->o4.f(), d->state.f(), d->z_in.f(), ip, d->noise_in.f(), N, T, cfg_scale,
+                                                                      reinterpret_cast<const StepConst*>(d->sched.p), step_ptr);
+            MB_LAUNCH_CHECK();
+        }
         dit_step_advance_kernel<<<1, 1, 0, s>>>(step_ptr);
         MB_LAUNCH_CHECK();
         g_launch_count += 3;
@@ -463,7 +522,7 @@ extern "C" int mb200_dit_sample_loop(mb200_dit* d, const float* z, const float* 
         for (int k = 0; k < steps; ++k) MB_TRY(one_step(st));
     } else {
         // the graph bakes (N, T, mask, in-paint on/off, cfg_scale, steps, the mods / noise table addresses)
-        const auto key = std::make_tuple((int)N, (int)T, (int)mk.mask_mode, (int)mk.band, (inpaint ? 1 : 0) + 2 * steps);
+        const auto key = std::make_tuple((int)N, (int)T, (int)mk.mask_mode, (int)mk.band + 4096 * d->n_sliders, (inpaint ? 1 : 0) + 2 * steps);
         if (d->graph_cfg_scale != cfg_scale || d->graph_noise != d->noise_in.p || d->graph_mods != d->mods.p) {
             for (auto& g : d->step_graphs) cudaGraphExecDestroy(g.second.first);
             d->step_graphs.clear();
@@ -494,6 +553,58 @@ extern "C" int mb200_dit_sample_loop(mb200_dit* d, const float* z, const float* 
         g_launch_count += (long long)steps * it->second.second;
     }
     MB_CUDA_CHECK(cudaMemcpyAsync(out, d->state.p, state_bytes, cudaMemcpyDeviceToDevice, st));
+    if (sl.n > 0) {
+        int herr = 0;
+        MB_CUDA_CHECK(cudaMemcpyAsync(&herr, d->sl_err.p, 4, cudaMemcpyDeviceToHost, st));
+        MB_CUDA_CHECK(cudaStreamSynchronize(st));
+        MB_REQUIRE(herr == 0, herr == 1 ? "a slider has more than 64 control points" : "a slider sub-path has more than 32 control points or needs more than 24 subdivision levels");
+    }
+    return 0;
+}
+
+// Sliders of the chunk about to be sampled (host arrays; n == 0 clears).  The caller filters them like the reference closure does
+// (all control points and the end event inside the chunk, diffusion_pipeline.py:211-212) and passes chunk-relative indices.
+extern "C" int mb200_dit_set_sliders(mb200_dit* d, int32_t n, const int32_t* cp_offsets, const int32_t* cp_index, const int32_t* end_index,
+                                     const int32_t* type, const float* length) {
+    MB_REQUIRE(d && d->finalized && n >= 0, "bad argument");
+    d->n_sliders = 0;
+    if (n == 0) return 0;
+    MB_REQUIRE(cp_offsets && cp_index && end_index && type && length, "null argument");
+    const int total = cp_offsets[n];
+    for (int k = 0; k < n; ++k) {
+        MB_REQUIRE(cp_offsets[k + 1] - cp_offsets[k] >= 1 && cp_offsets[k + 1] - cp_offsets[k] <= 64, "a slider needs 1..64 control points");
+        MB_REQUIRE(type[k] >= 0 && type[k] <= 3, "unknown curve type");
+        MB_REQUIRE(end_index[k] >= 0 && end_index[k] < d->cfg.max_seq_len, "slider end index outside the chunk");
+    }
+    for (int i = 0; i < total; ++i) MB_REQUIRE(cp_index[i] >= 0 && cp_index[i] < d->cfg.max_seq_len, "slider control point outside the chunk");
+    // buffers only ever grow to the chunk capacity once: a captured step graph holds their addresses
+    const size_t cap = (size_t)d->cfg.max_seq_len;
+    MB_REQUIRE((size_t)n <= cap && (size_t)total <= 8 * cap, "more sliders / control points than the chunk can hold");
+    MB_TRY(d->sl_off.ensure((cap + 1) * 4)); MB_TRY(d->sl_idx.ensure(8 * cap * 4)); MB_TRY(d->sl_end.ensure(cap * 4));
+    MB_TRY(d->sl_type.ensure(cap * 4)); MB_TRY(d->sl_len.ensure(cap * 4)); MB_TRY(d->sl_err.ensure(64));
+    MB_CUDA_CHECK(cudaMemcpy(d->sl_off.p, cp_offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice));
+    MB_CUDA_CHECK(cudaMemcpy(d->sl_idx.p, cp_index, (size_t)total * 4, cudaMemcpyHostToDevice));
+    MB_CUDA_CHECK(cudaMemcpy(d->sl_end.p, end_index, (size_t)n * 4, cudaMemcpyHostToDevice));
+    MB_CUDA_CHECK(cudaMemcpy(d->sl_type.p, type, (size_t)n * 4, cudaMemcpyHostToDevice));
+    MB_CUDA_CHECK(cudaMemcpy(d->sl_len.p, length, (size_t)n * 4, cudaMemcpyHostToDevice));
+    MB_CUDA_CHECK(cudaMemset(d->sl_err.p, 0, 4));
+    d->n_sliders = n;
+    return 0;
+}
+
+// The slider half of the closure on its own (Python-loop seam and parity tests): x DEVICE [N, 2, T] in place.
+extern "C" int mb200_dit_apply_sliders(mb200_dit* d, float* x, int32_t N, int32_t T, void* stream) {
+    MB_REQUIRE(d && d->finalized && x && N >= 1 && T >= 1 && T <= d->cfg.max_seq_len, "bad argument");
+    if (d->n_sliders == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_TRY(d->sl_pix.ensure((size_t)2 * d->cfg.max_seq_len * 4));
+    SliderSet sl{d->n_sliders, reinterpret_cast<const int*>(d->sl_off.p), reinterpret_cast<const int*>(d->sl_idx.p),
+                 reinterpret_cast<const int*>(d->sl_end.p), reinterpret_cast<const int*>(d->sl_type.p), d->sl_len.f()};
+    MB_TRY(launch_slider_recompute(sl, x, N, T, d->sl_pix.f(), reinterpret_cast<int*>(d->sl_err.p), st));
+    int herr = 0;
+    MB_CUDA_CHECK(cudaMemcpyAsync(&herr, d->sl_err.p, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    MB_REQUIRE(herr == 0, "slider path exceeds the device limits (64 control points, 32 per sub-path, 24 subdivision levels)");
     return 0;
 }
 

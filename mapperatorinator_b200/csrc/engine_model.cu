@@ -345,12 +345,14 @@ extern "C" int mb200_model_finalize(mb200_model* m) {
         auto al = [](size_t n) { return (n + 15) & ~size_t(15); };
         const size_t n_x = al((size_t)R2 * d), n_kv = al((size_t)R2 * 2 * d), n_h = al((size_t)R2 * f), n_l = al((size_t)R2 * c.vocab_size_out),
                      n_p = al((size_t)R2 * c.heads * max_splits * 66), n_hdr = 16;
-        m->ll_bytes = (3 * n_x + n_kv + n_h + n_l + n_p + n_hdr) * 8;
+        const size_t RM = MEGA_LL_MAX_REPS;
+        m->ll_bytes = ((2 * RM + 1) * n_x + n_kv + RM * n_h + n_l + n_p + n_hdr) * 8;
         MB_TRY(m->ll_arena.ensure(m->ll_bytes, true));
         unsigned long long* b = m->ll_arena.as<unsigned long long>();
-        m->ll.x = b; b += n_x; m->ll.q = b; b += n_x; m->ll.att = b; b += n_x; m->ll.kvnew = b; b += n_kv; m->ll.h = b; b += n_h;
+        m->ll.x = b; b += RM * n_x; m->ll.att = b; b += RM * n_x; m->ll.q = b; b += n_x; m->ll.kvnew = b; b += n_kv; m->ll.h = b; b += RM * n_h;
         m->ll.logits = b; b += n_l; m->ll.part = b; b += n_p; m->ll.hdr = b;
         m->ll.max_splits = max_splits;
+        m->ll.reps = 8; m->ll.x_rep = (long long)n_x; m->ll.h_rep = (long long)n_h;
     }
     m->finalized = true;
     return 0;
@@ -746,8 +748,10 @@ static int run_megakernel2(mb200_model* m, int rows, int B, int n_splits_self, i
     mp.sample = sample_params(m, rows); mp.st = m->g_state.as<GenState>();
     mp.ll = m->ll; mp.error_flag = m->g_megasync.as<int>() + 8;
     mp.sample.ll_logits = m->ll.logits; mp.sample.ll_x_out = m->ll.x; mp.sample.ll_hdr = m->ll.hdr; mp.sample.ll_err = mp.error_flag;
+    mp.sample.ll_reps = m->ll.reps; mp.sample.ll_x_rep = m->ll.x_rep;
     mp.max_steps = max_steps; mp.row_slot = m->g_rowslot.as<int>(); mp.x_in = m->d_x.as<float>();
     mp.rows = rows; mp.d_model = m->cfg.d_model; mp.V = m->cfg.vocab_size_out;
+    mp.trace = m->mega_trace.p ? m->mega_trace.as<unsigned long long>() : nullptr; mp.trace_step = 8;
     if (!m->mega_ev[0]) { MB_CUDA_CHECK(cudaEventCreate(&m->mega_ev[0])); MB_CUDA_CHECK(cudaEventCreate(&m->mega_ev[1])); }
     MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 2, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
     MB_CUDA_CHECK(cudaEventRecord(m->mega_ev[0], st));
@@ -994,6 +998,12 @@ extern "C" int mb200_model_set_option(mb200_model* m, const char* name, int valu
         return 0;
     }
     if (!strcmp(name, "mega")) { m->use_mega = value; return 0; }
+    if (!strcmp(name, "ll_sleep")) return mega2_set_poll_sleep(value);
+    if (!strcmp(name, "ll_reps")) {
+        MB_REQUIRE(value >= 1 && value <= MEGA_LL_MAX_REPS && value * 2 <= 32, "ll_reps must be in [1, 16]");
+        m->ll.reps = value;
+        return 0;
+    }
     if (!strcmp(name, "mega_trace")) {
         if (value) { MB_TRY(m->mega_trace.ensure(128 * 16 * 8)); MB_CUDA_CHECK(cudaMemset(m->mega_trace.p, 0, 128 * 16 * 8)); }
         return 0;

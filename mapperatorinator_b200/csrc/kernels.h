@@ -90,6 +90,19 @@ struct AttentionParams {
 };
 int launch_attention(const AttentionParams& p, cudaStream_t stream);
 
+// ---- slider.cu: slider end-point recompute of the diffusion denoised_fn (diffusion_pipeline.py:203-222) -------------------
+struct SliderSet {                 // device arrays describing the sliders that lie fully inside the current chunk
+    int n;
+    const int* cp_offsets;         // [n + 1] prefix offsets into cp_index
+    const int* cp_index;           // chunk-relative sequence index of every control point (head, anchors ..., last anchor)
+    const int* end_index;          // [n] chunk-relative sequence index of the slider-end event
+    const int* type;               // [n] 0 Bezier, 1 PerfectCurve, 2 Catmull, 3 Linear
+    const float* length;           // [n] slider length in osu! pixels
+};
+// x: DEVICE [N, 2, T] normalised coordinates, updated in place: conditional half -> pixels, every slider end moved to
+// position_at(length / max_length) of its path, pixels written back to BOTH halves.  pix_scratch: >= 2*T floats.
+int launch_slider_recompute(const SliderSet& sl, float* x, int N, int T, float* pix_scratch, int* error_flag, cudaStream_t st);
+
 // ---- mel.cu ----------------------------------------------------------------------------------------------------------
 struct MelPlan;   // opaque (filterbank in CSR form + twiddles on device)
 int mel_plan_create(MelPlan** out, int n_fft, int hop, int n_mels, int pad_reflect, int log_scale,
@@ -200,6 +213,7 @@ struct SampleParams {
     // as tagged pairs (see decode_mega2.cu)
     const unsigned long long* ll_logits; unsigned ll_in_tag;
     unsigned long long* ll_x_out; unsigned long long* ll_hdr; unsigned ll_out_tag;
+    int ll_reps; long long ll_x_rep;                // replicas of the residual-stream buffer and their stride (see MegaLL)
     int* ll_err;
 };
 int launch_sample(const SampleParams& p, int B, cudaStream_t stream, bool pdl);
@@ -243,7 +257,13 @@ struct MegaLL {                                   // engine-owned exchange buffe
     unsigned long long* part;                     // [rows][H][max_splits][66]  split-KV partials: o[64], m, l
     unsigned long long* hdr;                      // [0] cur_len, [1] all_finished of the NEXT token (written by the selection phase)
     int max_splits;
+    // x, att and h are read by (almost) every CTA.  148 SMs polling the same 6 KB turned its L2 lines into a hot spot (measured: the
+    // tagged stores took ~3 us to become visible under that read pressure), so these three buffers exist `reps` times; producers store
+    // every replica, CTA c polls replica c % reps.
+    int reps;
+    long long x_rep, h_rep;                       // replica strides of x / att (2 * d) and h (2 * ffn), in pairs
 };
+constexpr int MEGA_LL_MAX_REPS = 16;
 enum MegaLLSel : int { LL_NONE = 0, LL_X = 1, LL_Q = 2, LL_K = 3, LL_V = 4, LL_ATT = 5, LL_H = 6, LL_LOGITS = 7 };
 struct Mega2Phase {
     MegaPhase base;                               // the barrier kernel's descriptor (weights, segments, attention geometry, prefetch chain)
@@ -262,9 +282,11 @@ struct Mega2Params {
     const int* row_slot;
     const float* x_in;                            // [rows][d] plain residual stream left by the prefill's selection kernel
     int rows, d_model, V;
+    unsigned long long* trace; int trace_step;    // optional [4 CTAs][n_phases][4] clock64 stamps (tools/mega2_trace.py)
 };
 size_t mega2_smem_bytes();
 int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream);
+int mega2_set_poll_sleep(int ns);                 // tuning: nanoseconds to back off after a failed poll (0 = spin)
 
 // one-time per call: scan the prompt for the MonotonicTimeShift state (logit_processors.py:149-166)
 int launch_prompt_scan(const long long* ids, long long ids_ld, int B, int P, const unsigned char* vflags, int ts_start, int ts_end,

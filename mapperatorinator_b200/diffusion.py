@@ -21,15 +21,44 @@ from .config import DiTConfig, dit_b_config
 from .engine import DiTEngine
 
 
-class InpaintDenoiser:
-    """`denoised_fn` of `sample_part` without sliders: x0 <- where(mask, x0, z) (diffusion_pipeline.py:203-205).
-    Callable like the reference closure, and recognisable by the fused loop."""
+class DiffusionSlider:
+    """`DiffusionSlider` of the reference (diffusion_pipeline.py:30-35): sequence indices of the control points (head, anchors, last
+    anchor), sequence index of the slider-end event, curve type ('Bezier' | 'PerfectCurve' | 'Catmull'), length in osu! pixels."""
 
-    def __init__(self, mask: torch.Tensor, z: torch.Tensor):
+    def __init__(self, seq_indices, end_index: int, curve_type: Optional[str], length: float):
+        self.seq_indices = np.asarray(seq_indices, dtype=np.int64)
+        self.end_index, self.curve_type, self.length = int(end_index), curve_type, float(length)
+
+
+class InpaintDenoiser:
+    """`denoised_fn` of `sample_part` (diffusion_pipeline.py:203-222): x0 <- where(mask, x0, z), then — when the chunk contains sliders
+    — every slider end moved to `SliderPath(curve_type, control points).position_at(length / max_length)` computed from the
+    conditional half, and the positions written back to both halves.  Callable like the reference closure (the slider part runs on the
+    device through `engine`), and recognisable by the fused loop, which then keeps all 100 steps on the device.
+    `sliders`: DiffusionSlider objects with ABSOLUTE sequence indices; `start` / `end`: the chunk's range — sliders that are not fully
+    inside are skipped exactly like the reference does (:211-212)."""
+
+    def __init__(self, mask: torch.Tensor, z: torch.Tensor, sliders=None, start: int = 0, end: Optional[int] = None, engine=None):
         self.mask, self.z = mask, z
+        end = start + z.shape[-1] if end is None else end
+        self.chunk_sliders = []
+        for s in sliders or []:
+            if np.any((s.seq_indices < start) | (s.seq_indices >= end)) or s.end_index < start or s.end_index >= end:
+                continue
+            self.chunk_sliders.append((s.curve_type, s.seq_indices - start, s.end_index - start, s.length))
+        self.engine = engine
+        ends = [c[2] for c in self.chunk_sliders]
+        cps = set(int(i) for c in self.chunk_sliders for i in c[1])
+        assert len(set(ends)) == len(ends) and not (set(ends) & cps), \
+            "slider end events must be distinct and must not be control points of other sliders (the device recompute is parallel)"
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        return torch.where(self.mask, x, self.z)
+        x = torch.where(self.mask, x, self.z)
+        if self.chunk_sliders:
+            assert self.engine is not None, "pass engine=B200DiT.engine to recompute slider ends outside the fused loop"
+            self.engine.set_sliders(self.chunk_sliders)
+            x = self.engine.apply_sliders(x.to(self.engine.device)).to(x.device)
+        return x
 
 
 def _classify_mask(attn_mask: Optional[torch.Tensor]):
@@ -188,8 +217,13 @@ class SpacedDiffusion:
             ip = None if denoised_fn is None else denoised_fn.mask.to(dev)
             z = img.to(dev) if denoised_fn is None else denoised_fn.z.to(dev)
             assert denoised_fn is None or torch.equal(z, img.to(dev)), "fused loop in-paints from the start state"
-            return owner.engine.sample_loop(img.to(dev), mk["c"].to(dev), mk["y"].to(dev), float(mk.get("cfg_scale", 1.0)),
-                                            self.schedule_rows(), step_noise.to(dev), ip, mode, band, dense)
+            # sliders of this chunk: the engine applies the closure to the start state (diffusion_pipeline.py:233) and to every step
+            owner.engine.set_sliders(getattr(denoised_fn, "chunk_sliders", None))
+            try:
+                return owner.engine.sample_loop(img.to(dev), mk["c"].to(dev), mk["y"].to(dev), float(mk.get("cfg_scale", 1.0)),
+                                                self.schedule_rows(), step_noise.to(dev), ip, mode, band, dense)
+            finally:
+                owner.engine.set_sliders(None)
         for k, i in enumerate(range(n - 1, -1, -1)):
             t = torch.tensor([i] * shape[0], device=img.device)
             out = self.p_sample(model, img, t, clip_denoised, denoised_fn, cond_fn, mk, None if step_noise is None else step_noise[k])
@@ -222,8 +256,8 @@ def band_attention_mask(seq_len: int, width: int, device=None) -> torch.Tensor:
 def sample_sequence(dit: "B200DiT", seq_x: torch.Tensor, seq_c: torch.Tensor, y: torch.Tensor, y_null: torch.Tensor,
                     cfg_scale: float = 1.0, timesteps=(100, 0, 0, 0, 0, 0, 0, 0, 0, 0), diffusion_steps: int = 1000,
                     noise_schedule: str = "squaredcos_cap_v2", train_seq_len: int = 128, max_seq_len: int = 1024,
-                    overlap_buffer: int = 128, step_noise: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
-    """The slider-free body of `DiffisionPipeline.generate` (diffusion_pipeline.py:139-287): CFG batch, band mask, chunks of
+                    overlap_buffer: int = 128, step_noise: Optional[Sequence[torch.Tensor]] = None, sliders=None) -> torch.Tensor:
+    """The body of `DiffisionPipeline.generate` (diffusion_pipeline.py:139-287; `sliders` = its DiffusionSlider list): CFG batch, band mask, chunks of
     `max_seq_len` with `overlap_buffer` frozen / re-noised margins, in-paint mask, 100-step refinement of every chunk on
     the device, then `to_positions` (x (512, 384)).  seq_x (2, T) in [-1, 1], seq_c (272, T), y / y_null (C,).
     `step_noise[k]` optionally injects chunk k's noise tensor (steps, 2, 2, T_k) for parity runs.  Returns (2, T) osu! pixels."""
@@ -245,7 +279,8 @@ def sample_sequence(dit: "B200DiT", seq_x: torch.Tensor, seq_c: torch.Tensor, y:
         mask[:, :, (overlap_buffer if i > 0 else 0):] = True
         mk = dict(c=c[:, :, i:end].contiguous(), y=yy, cfg_scale=cfg_scale, attn_mask=attn_mask[i:end, i:end].contiguous(),
                   key_padding_mask=None)
-        out = diffusion.p_sample_loop(dit.forward_with_cfg, z_part.shape, z_part, denoised_fn=InpaintDenoiser(mask, z_part),
+        out = diffusion.p_sample_loop(dit.forward_with_cfg, z_part.shape, z_part,
+                                      denoised_fn=InpaintDenoiser(mask, z_part, sliders, start=i, end=end, engine=dit.engine),
                                       clip_denoised=True, model_kwargs=mk, step_noise=None if step_noise is None else step_noise[k])
         full[:, :, i:end] = out
         k += 1

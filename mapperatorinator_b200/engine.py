@@ -281,6 +281,33 @@ class DiTEngine:
                                                       sched.ctypes.data, steps, noise.data_ptr(), out.data_ptr(), _stream()))
         return out
 
+    CURVE_TYPES = {"Bezier": 0, "PerfectCurve": 1, "Catmull": 2, "Linear": 3, None: 0}
+
+    def set_sliders(self, sliders) -> int:
+        """Register the sliders of the chunk about to be sampled: iterable of (curve_type, control-point indices, end index, length)
+        with CHUNK-RELATIVE indices (empty / None clears).  Returns how many were registered."""
+        sl = list(sliders or [])
+        if not sl:
+            _lib.check(self.lib.mb200_dit_set_sliders(self.handle, 0, None, None, None, None, None))
+            return 0
+        off = np.zeros(len(sl) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(s[1]) for s in sl])
+        idx = np.ascontiguousarray(np.concatenate([np.asarray(s[1], dtype=np.int32) for s in sl]))
+        end = np.ascontiguousarray([int(s[2]) for s in sl], dtype=np.int32)
+        typ = np.ascontiguousarray([self.CURVE_TYPES.get(s[0], 0) for s in sl], dtype=np.int32)      # anything unknown flattens as a bezier (slider_path.py:114-115)
+        length = np.ascontiguousarray([float(s[3]) for s in sl], dtype=np.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mb200_dit_set_sliders(self.handle, len(sl), off.ctypes.data, idx.ctypes.data, end.ctypes.data, typ.ctypes.data,
+                                                      length.ctypes.data))
+        return len(sl)
+
+    def apply_sliders(self, x: torch.Tensor) -> torch.Tensor:
+        """The slider half of the `denoised_fn` closure on x (N, 2, T) CUDA f32 (returns a new tensor)."""
+        x = x.contiguous().float().clone()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mb200_dit_apply_sliders(self.handle, x.data_ptr(), x.shape[0], x.shape[2], _stream()))
+        return x
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):

@@ -152,8 +152,38 @@ def main():
     dit_out["schedule"] = np.stack([diff.sqrt_recip_alphas_cumprod, diff.sqrt_recipm1_alphas_cumprod, diff.posterior_log_variance_clipped,
                                     np.log(diff.betas), diff.posterior_mean_coef1, diff.posterior_mean_coef2], 1)
     np.savez_compressed(os.path.join(OUT, "dit_reference.npz"), **dit_out, **{f"meta_{k}": v for k, v in meta.items()})
+    make_slider_golden(meta)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def make_slider_golden(meta=None):
+    """Slider end points from the UNMODIFIED reference `SliderPath` (osuT5/osuT5/inference/slider_path.py) on (a) every slider of the
+    reference's own toy beatmap (osu_diffusion/testing/toy_datasets/kimi_no_bouken.osu: 138 sliders, Bezier / PerfectCurve / Linear, with
+    red anchors) and (b) seeded random control points for all curve types incl. Catmull.  Stored: control points (float32, as the pipeline
+    feeds them), curve type, length, reference max_length and end position."""
+    from oracle import ref_import, slider as so
+    SP = ref_import.reference_slider_path()
+    cases_ = [(t, c, l) for t, c, l in so.parse_osu_sliders(os.path.join(ref_import.REFERENCE_ROOT, "osu_diffusion", "testing", "toy_datasets", "kimi_no_bouken.osu"))]
+    rng = np.random.default_rng(42)
+    for typ in ("Bezier", "PerfectCurve", "Catmull"):
+        for k in range(40):
+            ncp = int(rng.integers(2, 9)) if typ != "PerfectCurve" else int(rng.choice([3, 3, 3, 4, 2]))
+            cps = (rng.random((ncp, 2)) * np.array([512, 384])).astype(np.float32)
+            if typ == "Bezier" and ncp >= 4 and k % 3 == 0:
+                j = int(rng.integers(1, ncp - 2)); cps[j + 1] = cps[j]                      # red anchor
+            cases_.append((typ, cps, float(rng.random() * 400 + 10)))
+    types, offs, pts, lens, maxl, ends = [], [0], [], [], [], []
+    for typ, cps, length in cases_:
+        sp = SP(typ, cps)
+        ml = float(sp.get_distance())
+        if ml == 0:
+            continue
+        e = np.asarray(sp.position_at(length / ml), dtype=np.float64)
+        types.append(so.CURVE_TYPES[typ]); offs.append(offs[-1] + len(cps)); pts.append(cps); lens.append(length); maxl.append(ml); ends.append(e)
+    np.savez_compressed(os.path.join(OUT, "slider_reference.npz"), types=np.array(types, dtype=np.int32), offsets=np.array(offs, dtype=np.int32),
+                        points=np.concatenate(pts).astype(np.float32), lengths=np.array(lens, dtype=np.float32), max_length=np.array(maxl),
+                        end_pos=np.stack(ends), **({f"meta_{k}": v for k, v in (meta or {}).items()}))
 
 
 if __name__ == "__main__":
