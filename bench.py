@@ -265,7 +265,7 @@ def main() -> None:
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("MB200_PDL", "0")))
     ap.add_argument("--windows", type=int, default=0, help="debug: truncate the song to this many windows")
     ap.add_argument("--tc", type=int, default=int(os.environ.get("MB200_TC", "1")), help="1 = tcgen05 3xTF32 GEMMs where eligible, 0 = fp32 SIMT GEMM everywhere")
-    ap.add_argument("--mega", type=int, default=2, help="2 = dataflow token-loop megakernel (default), 1 = grid-barrier megakernel, 0 = CUDA-graph replay per token")
+    ap.add_argument("--mega", type=int, default=3, help="3 = dataflow token-loop megakernel with K-split GEMV phases (default), 2 = dataflow with row-per-warp GEMV phases, 1 = grid-barrier megakernel, 0 = CUDA-graph replay per token")
     ap.add_argument("--cpu-threads", type=int, default=int(os.environ.get("MB200_CPU_THREADS", "0")),
                     help="torch threads of the CPU arm (0 = min(cores, 16): measured best on the GPU box; 32+ threads slow a batch-1 decoder down)")
     args = ap.parse_args()
@@ -444,7 +444,7 @@ def main() -> None:
         us_per_launch = 1000.0 * mega[1] / mega[0]
         bytes_per_launch = (w_bytes + kv_bytes) * tok_per_launch
         achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9
-        roofline = {"bound": "hbm", "kernel": ("decode_megakernel_ll<1> (dataflow megakernel" if args.mega == 2 else "decode_megakernel<1> (grid-barrier megakernel")
+        roofline = {"bound": "hbm", "kernel": ("decode_megakernel_ll<1> (dataflow megakernel" if args.mega >= 2 else "decode_megakernel<1> (grid-barrier megakernel")
                               + ": persistent cooperative kernel, all layers of all tokens of one generate() call)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic if traffic and abs(tok_per_launch - 63.0) < 1e-6 else None, "traffic_source": traffic_src,

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleParams p) 
     pdl_launch_dependents();
     pdl_wait();
     if (p.st->all_finished) return;   // replays past the end of a call are no-ops (uniform across the grid)
-    sample_body(p, blockIdx.x, sm);
+    sample_body<SAMPLE_THREADS>(p, blockIdx.x, sm);
 }
 
 __global__ void prompt_scan_kernel(const long long* ids, long long ids_ld, int P, const unsigned char* vflags, int ts_start, int ts_end,

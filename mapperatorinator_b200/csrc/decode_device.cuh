@@ -29,7 +29,12 @@ static __constant__ int c_ll_sleep_ns = 0;      // tuning knob (engine option "l
 constexpr long long LL_SPIN_LIMIT = 1ll << 24;      // ~ seconds; a dataflow wait that long is a bug, never a slow producer
 // Wait for one / two / four consecutive pairs carrying `tag`.  Bounded: on a timeout (or when another CTA raised `err`) the error flag is
 // set and zeros are returned, so a logic error ends the launch instead of hanging the GPU.
+// diagnostics only (engine option "ll_debug", tools/mega2_trace.py): bit 0 = no weight copies, bit 1 = polls never wait (whatever is in the
+// exchange buffer is taken), bit 2 = GEMV phases skip their multiply-reduce.  Any bit set -> the tokens are garbage, the TIMING tells
+// which part of a phase the time goes to.
+static __constant__ int c_ll_debug = 0;
 __device__ __forceinline__ bool ll_spin_check(long long& spin, int* err) {
+    if (c_ll_debug & 2) return false;
     if (c_ll_sleep_ns > 0) __nanosleep((unsigned)c_ll_sleep_ns);
     if ((++spin & 0x3FF) == 0 && (spin > LL_SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0)) { atomicCAS(err, 0, 4); return false; }
     return true;
@@ -605,6 +610,7 @@ __device__ __forceinline__ void decode_attention_warp_body(const DecAttnParams& 
 constexpr int SAMPLE_THREADS = 512;
 constexpr int VMAX = 4096;
 
+template <int NT>
 static __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = is_max ? warp_max(v) : warp_sum(v);
@@ -612,7 +618,7 @@ static __device__ __forceinline__ float block_reduce(float v, bool is_max, float
     if (lane == 0) scratch[warp] = v;
     __syncthreads();
     if (warp == 0) {
-        float t = lane < SAMPLE_THREADS / 32 ? scratch[lane] : (is_max ? -INFINITY : 0.f);
+        float t = lane < NT / 32 ? scratch[lane] : (is_max ? -INFINITY : 0.f);
         t = is_max ? warp_max(t) : warp_sum(t);
         if (lane == 0) scratch[32] = t;
     }
@@ -636,11 +642,13 @@ struct SampleSmem {
     int wi[SAMPLE_THREADS / 32];
 };
 
-// The whole logits-processor chain + token selection + append for batch row b (one CTA of SAMPLE_THREADS threads).
+// The whole logits-processor chain + token selection + append for batch row b (one CTA of NT threads).
 // Deliberately NOT inlined and with rolled vocabulary loops: it runs once per token on one CTA; inlined and unrolled it was 70 KB of
 // the megakernel's 130 KB of code.  (A cold/warm re-run experiment later showed the per-layer phases are NOT instruction-fetch bound,
 // so this is about code size and register pressure of the caller, not about the 32 KB L1.5 instruction cache.)
 // Returns after the "last CTA" bookkeeping; the caller decides how the grid synchronises afterwards.
+// NT = threads of the calling CTA (512 in the per-phase kernel and the barrier megakernel, 256 in the dataflow megakernel).
+template <int NT>
 static __device__ __noinline__ void sample_body(const SampleParams& p, int b, SampleSmem& sm) {
     float* s = sm.s;
     int* sidx = sm.sidx;
@@ -658,7 +666,7 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
     // (0)+(1): min_new_tokens EOS suppression, then classifier-free guidance on raw logits
     if (p.ll_logits) {
         // dataflow megakernel: logits arrive as tagged pairs; all of a thread's pairs are requested before the first tag is examined
-        constexpr int PER = VMAX / SAMPLE_THREADS;
+        constexpr int PER = VMAX / NT;
         float cond[PER];
         for (int half = 0; half < (c.use_cfg ? 2 : 1); ++half) {      // conditional rows, then (CFG only) the unconditional rows
             ll_t w[PER];
@@ -668,19 +676,19 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
                 bool ok = true;
 #pragma unroll
                 for (int j = 0; j < PER; ++j) {
-                    const int v = tid + j * SAMPLE_THREADS;
+                    const int v = tid + j * NT;
                     if (v < V) asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w[j]) : "l"(src + v) : "memory");
                 }
 #pragma unroll
                 for (int j = 0; j < PER; ++j) {
-                    const int v = tid + j * SAMPLE_THREADS;
+                    const int v = tid + j * NT;
                     if (v < V) ok = ok && (unsigned)(w[j] >> 32) == p.ll_in_tag;
                 }
                 if (ok || !ll_spin_check(spin, p.ll_err)) break;
             }
 #pragma unroll
             for (int j = 0; j < PER; ++j) {
-                const int v = tid + j * SAMPLE_THREADS;
+                const int v = tid + j * NT;
                 if (v < V) {
                     const float x = __uint_as_float((unsigned)w[j]);
                     if (half == 0) cond[j] = x;                            // first half = "conditional" in HF's processor
@@ -693,7 +701,7 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
             }
         }
     } else {
-    _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
+    _Pragma("unroll 1") for (int v = tid; v < V; v += NT) {
         float x;
         const bool eos = (p.vflags[v] & VF_EOS) != 0;
         if (c.use_cfg) {
@@ -720,7 +728,7 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         }
     }
     __syncthreads();
-    _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
+    _Pragma("unroll 1") for (int v = tid; v < V; v += NT) {
         float x = s[v];
         if (v >= c.ts_start && v < c.ts_end) {
             if (lts >= 0 && v < c.ts_start + lts) x = -INFINITY;
@@ -733,36 +741,36 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
     // (5) LookbackBias
     if (c.lookback_on) {
         if (!c.types_first) {
-            _Pragma("unroll 1") for (int v = c.lookback_start + tid; v < c.lookback_end; v += SAMPLE_THREADS) s[v] = -INFINITY;
+            _Pragma("unroll 1") for (int v = c.lookback_start + tid; v < c.lookback_end; v += NT) s[v] = -INFINITY;
             __syncthreads();
         } else {
             float* ls_cur = p.last_scores + ((long long)(st_step & 1) * B + b) * V;
             const float* ls_prev = p.last_scores + ((long long)((st_step + 1) & 1) * B + b) * V;
-            _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) ls_cur[v] = s[v];
+            _Pragma("unroll 1") for (int v = tid; v < V; v += NT) ls_cur[v] = s[v];
             const long long last_tok = L > 0 ? __ldcg(ids_row + (L - 1)) : -1;
             const bool timed = last_tok >= 0 && (p.vflags[last_tok] & VF_TIMED);
             if (st_has_last && timed) {
                 float m_last = -INFINITY, m_cur = -INFINITY;
-                _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) { m_last = fmaxf(m_last, __ldcg(ls_prev + v)); m_cur = fmaxf(m_cur, s[v]); }
-                m_last = block_reduce(m_last, true, scratch);
-                m_cur = block_reduce(m_cur, true, scratch);
+                _Pragma("unroll 1") for (int v = tid; v < V; v += NT) { m_last = fmaxf(m_last, __ldcg(ls_prev + v)); m_cur = fmaxf(m_cur, s[v]); }
+                m_last = block_reduce<NT>(m_last, true, scratch);
+                m_cur = block_reduce<NT>(m_cur, true, scratch);
                 float z_last = 0.f, z_cur = 0.f, e_last = 0.f, o_cur = 0.f;
-                _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
+                _Pragma("unroll 1") for (int v = tid; v < V; v += NT) {
                     float pl = expf(__ldcg(ls_prev + v) - m_last);
                     float pc = expf(s[v] - m_cur);
                     z_last += pl; z_cur += pc;
                     if (p.vflags[v] & VF_LB_EOS) e_last += pl;
                     if (!(v >= c.lookback_start && v < c.lookback_end)) o_cur += pc;
                 }
-                z_last = block_reduce(z_last, false, scratch);
-                z_cur = block_reduce(z_cur, false, scratch);
-                e_last = block_reduce(e_last, false, scratch);
-                o_cur = block_reduce(o_cur, false, scratch);
+                z_last = block_reduce<NT>(z_last, false, scratch);
+                z_cur = block_reduce<NT>(z_cur, false, scratch);
+                e_last = block_reduce<NT>(e_last, false, scratch);
+                o_cur = block_reduce<NT>(o_cur, false, scratch);
                 const float prob_eos = e_last / z_last;
                 const float prob_event = 1.f - prob_eos;
                 const float sc = 1.f / ((o_cur / z_cur) * prob_event + prob_eos);
                 const float extra = fminf(fmaxf((sc - 1.f) * prob_eos / prob_event, 0.f), 1.f);
-                _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
+                _Pragma("unroll 1") for (int v = tid; v < V; v += NT) {
                     float pr;
                     if (v == c.lookback_start) pr = extra;
                     else if (v >= c.lookback_start && v < c.lookback_end) pr = 0.f;
@@ -777,10 +785,10 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
     // (6)-(7) selection
     int chosen = 0;
     if (!c.do_sample) {
-        if (p.dbg_scores) { _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) p.dbg_scores[(long long)b * V + v] = s[v]; }
+        if (p.dbg_scores) { _Pragma("unroll 1") for (int v = tid; v < V; v += NT) p.dbg_scores[(long long)b * V + v] = s[v]; }
         // argmax, first index on ties (torch.argmax)
         float best = -INFINITY; int bi = 0x7fffffff;
-        _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) {
+        _Pragma("unroll 1") for (int v = tid; v < V; v += NT) {
             float x = s[v];
             if (x > best || (x == best && v < bi)) { best = x; bi = v; }
         }
@@ -795,7 +803,7 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         if ((tid & 31) == 0) { wb[tid >> 5] = best; wi[tid >> 5] = bi; }
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
+            for (int w = 1; w < NT / 32; ++w)
                 if (wb[w] > best || (wb[w] == best && wi[w] < bi)) { best = wb[w]; bi = wi[w]; }
             sm.chosen_sh = (bi == 0x7fffffff) ? 0 : bi;
         }
@@ -803,13 +811,13 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         chosen = sm.chosen_sh;
     } else {
         // sort ascending (bitonic over VMAX slots, padding = +inf at the top so real entries keep ascending order)
-        _Pragma("unroll 1") for (int v = tid; v < VMAX; v += SAMPLE_THREADS) { sidx[v] = v; if (v >= V) s[v] = INFINITY; }
+        _Pragma("unroll 1") for (int v = tid; v < VMAX; v += NT) { sidx[v] = v; if (v >= V) s[v] = INFINITY; }
         __syncthreads();
         const bool need_sort = c.top_k > 0 || c.top_p < 1.0f;
         if (need_sort) {
             for (int k = 2; k <= VMAX; k <<= 1) {
                 for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < VMAX; i += SAMPLE_THREADS) {
+                    for (int i = tid; i < VMAX; i += NT) {
                         int ixj = i ^ j;
                         if (ixj > i) {
                             bool up = (i & k) == 0;
@@ -827,18 +835,18 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
                 int kk = min(c.top_k, V);
                 float thr = s[V - kk];
                 __syncthreads();
-                _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) if (s[v] < thr) s[v] = -INFINITY;
+                _Pragma("unroll 1") for (int v = tid; v < V; v += NT) if (s[v] < thr) s[v] = -INFINITY;
                 __syncthreads();
             }
         }
         // softmax statistics over the (possibly sorted) entries
         float m = -INFINITY;
-        _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) m = fmaxf(m, s[v]);
-        m = block_reduce(m, true, scratch);
+        _Pragma("unroll 1") for (int v = tid; v < V; v += NT) m = fmaxf(m, s[v]);
+        m = block_reduce<NT>(m, true, scratch);
         // Inclusive prefix sums of e[v] = exp(s[v] - m) in array order (ascending scores when sorted) by a block scan: thread t owns
         // the contiguous segment [t*SEG, (t+1)*SEG) (sequential inside, like the serial walk it replaces), warp shuffles scan the
         // segment totals, one warp scans the 16 warp totals.  The three serial thread-0 passes over V with expf (round 1) are gone.
-        constexpr int SEG = VMAX / SAMPLE_THREADS;
+        constexpr int SEG = VMAX / NT;
         const int lane = tid & 31, warp = tid >> 5;
         float loc[SEG];
         float run = 0.f;
@@ -859,7 +867,7 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         if (lane == 31) scratch[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            float w = lane < SAMPLE_THREADS / 32 ? scratch[lane] : 0.f;
+            float w = lane < NT / 32 ? scratch[lane] : 0.f;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const float t = __shfl_up_sync(0xffffffffu, w, o);
@@ -869,7 +877,7 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         }
         __syncthreads();
         const float base = (incl - run) + (warp > 0 ? scratch[warp - 1] : 0.f);
-        const float z = scratch[SAMPLE_THREADS / 32 - 1];
+        const float z = scratch[NT / 32 - 1];
         __syncthreads();
         // top-p (HF TopPLogitsWarper, min_tokens_to_keep = 1): in ascending order remove the longest prefix whose cumulative probability
         // is <= 1 - top_p; the last (largest) entry always stays.  The prefix sums are monotone, so its length is a count.
@@ -882,10 +890,10 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
                 const int v = tid * SEG + j;
                 if (v < V - 1 && (base + loc[j]) / z <= cut) cnt += 1.f;
             }
-            first_keep = (int)block_reduce(cnt, false, scratch);
+            first_keep = (int)block_reduce<NT>(cnt, false, scratch);
         }
         if (p.dbg_scores) {       // parity hook (tests): the scores the selection sees, -inf = removed by top-k / top-p, original id order
-            _Pragma("unroll 1") for (int v = tid; v < V; v += SAMPLE_THREADS) p.dbg_scores[(long long)b * V + sidx[v]] = v < first_keep ? -INFINITY : s[v];
+            _Pragma("unroll 1") for (int v = tid; v < V; v += NT) p.dbg_scores[(long long)b * V + sidx[v]] = v < first_keep ? -INFINITY : s[v];
         }
         // mass below the kept set, then inverse-CDF draw over the kept entries
         if (tid == 0) scratch[33] = 0.f;
@@ -903,7 +911,7 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
             const int v = tid * SEG + j;
             if (v >= first_keep && v < V && base + loc[j] < u) cnt += 1.f;
         }
-        const int pick = min(V - 1, first_keep + (int)block_reduce(cnt, false, scratch));
+        const int pick = min(V - 1, first_keep + (int)block_reduce<NT>(cnt, false, scratch));
         if (tid == 0) sm.chosen_sh = sidx[pick];
         __syncthreads();
         chosen = sm.chosen_sh;
@@ -931,7 +939,7 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         const float4* te = reinterpret_cast<const float4*>(p.tok_emb + tok * p.d_model);
         const float4* pe = reinterpret_cast<const float4*>(p.pos_emb + (long long)pos * p.d_model);
         float4* xo = reinterpret_cast<float4*>(p.x_out + (long long)row * p.x_ld);
-        for (int i = tid; i < p.d_model / 4; i += SAMPLE_THREADS) {
+        for (int i = tid; i < p.d_model / 4; i += NT) {
             float4 a = te[i], q = pe[i];
             const float4 o = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
             xo[i] = o;

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_megakernel(MegaParams 
                     __syncthreads();
                 }
             } else {
-                if (cta < sm.sample_params.cfg->B) sample_body(sm.sample_params, cta, sm.u.sample);
+                if (cta < sm.sample_params.cfg->B) sample_body<SAMPLE_THREADS>(sm.sample_params, cta, sm.u.sample);
             }
             MEGA_TRACE(11);
             asm volatile("cp.async.wait_all;" ::: "memory");

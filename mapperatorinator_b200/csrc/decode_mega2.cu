@@ -32,6 +32,8 @@ constexpr int M2_NB_MAX = 2;
 constexpr int M2_XS_FLOATS = M2_NB_MAX * 3072;
 constexpr int M2_XRAW_FLOATS = M2_NB_MAX * 1024;
 constexpr int M2_PART = 66;                             // pairs per split partial: o[64], m, l
+constexpr int M3_SLOTS = 16;                            // K-split GEMV: output rows per thread (row slots), two passes of 8
+constexpr int M3_ROWS = 32;                             // K-split GEMV: output rows per CTA and phase
 
 struct __align__(16) M2Smem {
     float wbuf[2][MEGA_WBUF_FLOATS];
@@ -41,10 +43,13 @@ struct __align__(16) M2Smem {
         struct { __align__(16) float sc[128]; float red[4][64]; __align__(16) float qs[64]; float kns[64]; float vns[64]; float stat[2]; } attn;
     } u;
     __align__(16) float xraw[M2_XRAW_FLOATS];   // raw residual stream as of this CTA's last LayerNorm staging (residual source of its rows)
-    Mega2Phase phase[2];
+    Mega2Phase phase[3];                        // descriptor of phase i lives in slot i % 3 (the K-split mode has no end-of-phase barrier)
     SampleParams sample_params;
     int ctrl[8];                                // cur_len, all_finished, error, prompt_len, encoder slots
     float ln_red[32];
+    // K-split GEMV mode (MODE 1): warp partial sums [parity][decoder row][row slot][warp] and the second LayerNorm statistic
+    __align__(16) float red[2][M2_NB_MAX][M3_ROWS][M2_WARPS];     // [phase parity][decoder row][output row of this CTA][warp of the row's group]
+    float ln_red2[32];
     unsigned long long mbar[2];
 };
 
@@ -78,7 +83,7 @@ __device__ __forceinline__ void prefetch_weights(const float* W, long long ldw, 
     int r0, r1;
     cta_rows(N, cta, rpc, r0, r1);
     const unsigned bytes = (unsigned)(r1 - r0) * (unsigned)K * 4u;
-    if (bytes == 0) { mbar_arrive(bar); return; }
+    if (bytes == 0 || (c_ll_debug & 1)) { mbar_arrive(bar); return; }
     mbar_arrive_expect_tx(bar, bytes);
     bulk_g2s(dst, W + (long long)r0 * ldw, bytes, bar);
 }
@@ -396,9 +401,343 @@ __device__ __forceinline__ void m2_attention_merge(const DecAttnParams& p, const
     for (int rep = 0; rep < ll.reps; ++rep) ll_store(ll.att + rep * ll.x_rep + (long long)r * d + h * 64 + tid, o, tag);
 }
 
+
+// ---- K-split GEMV phase (MODE 1) ---------------------------------------------------------------------------------------------------
+// The row-per-warp form spends its time in shared memory: every output row re-reads the whole activation vector next to its weight
+// row (2 x K x 4 bytes per row through a 128 B / clk port), only rows-per-CTA of the 16 warps have work (6 of 16 for the d x d
+// projections), and the activation takes a detour through shared memory behind two or three CTA barriers.  Here the CTA's weight slab
+// [R rows x K] is split along K instead: thread t owns float4 column(s) kq of EVERY row, keeps its 4 activation values in registers
+// (polled straight from the exchange buffer: no staging pass), and the R partial sums per thread are reduced by a transposing warp
+// butterfly (9 shuffles per 8 rows) plus one pass over <= 16 warp partials.  Summation order is fixed by the thread mapping.
+//   K4 = K / 4 float4 columns.  "grouped" (K4 a multiple of 32, <= 256: the d_model-wide inputs): G = 512 / K4 row groups, group rg
+//   takes rows rg, rg + G, ... and group 0 polls the activation for everybody (one CTA barrier).  Otherwise one group, thread t owns
+//   columns t and t + 512 (K4 <= 1024) and polls exactly what it multiplies.
+__device__ __forceinline__ float m3_dot4(const float4 w, const float4 x) {
+    float t0 = w.x * x.x; t0 = fmaf(w.y, x.y, t0);
+    float t1 = w.z * x.z; t1 = fmaf(w.w, x.w, t1);
+    return t0 + t1;
+}
+__device__ __forceinline__ float m3_tree8(const float* r) { return ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7])); }
+
+// 8 values per lane -> lane L (L % 4 == 0) holds the warp-wide sum of value index ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1)
+__device__ __forceinline__ float m3_reduce8(const float (&a)[8], int lane) {
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+    float b[4], c[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h16 ? a[i] : a[i + 4], keep = h16 ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h8 ? b[i] : b[i + 2], keep = h8 ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = h4 ? c[0] : c[1], keep = h4 ? c[1] : c[0];
+    float v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// Thread -> weight-column mapping of a K-wide input; K takes two values per model (d_model, ffn_dim): computed once per kernel.
+struct M3Map { int K4, G, rg, kq0, NS, npw, wi; bool grouped, in_group, active_warp; };
+__device__ __forceinline__ M3Map m3_make_map(int K, int tid) {
+    M3Map m;
+    m.K4 = K >> 2;
+    m.grouped = (m.K4 & 31) == 0 && m.K4 <= 256;
+    m.G = m.grouped ? M2_THREADS / m.K4 : 1;
+    m.rg = m.grouped ? tid / m.K4 : 0;
+    m.kq0 = tid - m.rg * m.K4;
+    m.in_group = m.rg < m.G;
+    m.NS = m.grouped ? 1 : (m.K4 + M2_THREADS - 1) / M2_THREADS;
+    m.npw = m.grouped ? m.K4 >> 5 : min(M2_WARPS, (m.K4 + 31) >> 5);
+    m.wi = m.grouped ? (tid >> 5) - m.rg * m.npw : (tid >> 5);
+    m.active_warp = m.grouped ? m.in_group : (tid >> 5) < m.npw;
+    return m;
+}
+
+// One pass of <= 8 row slots: all weight loads first (branch-free: out-of-range rows re-read row 0 and are discarded by a select),
+// then the products, then the transposing butterfly.  Everything a phase does is a chain of dependent latencies, so no load may sit
+// behind a branch that waits for the previous row's arithmetic.
+template <int NB, int NS>
+__device__ __forceinline__ void m3_pass(const float* wb, int K, int R, int G, int rg, int p0, const int (&kqc)[2], const float4 (&xv)[NB][2],
+                                        float* red_b0, float* red_b1, int wi, int lane) {
+    float acc[NB][8];
+    float4 w[8][NS];
+    bool valid[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int lr = (p0 + i) * G + rg;
+        valid[i] = lr < R;
+        const float4* wrow = reinterpret_cast<const float4*>(wb + (valid[i] ? lr : 0) * K);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) w[i][s] = wrow[kqc[s]];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float a = m3_dot4(w[i][0], xv[b][0]);
+            if (NS > 1) a += m3_dot4(w[i][NS - 1], xv[b][NS - 1]);
+            acc[b][i] = valid[i] ? a : 0.f;
+        }
+    }
+    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const int lr = (p0 + ridx) * G + rg;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const float v = m3_reduce8(acc[b], lane);
+        if ((lane & 3) == 0 && lr < R) (b == 0 ? red_b0 : red_b1)[lr * M2_WARPS + wi] = v;
+    }
+}
+
+template <int NB, typename SM>
+__device__ __forceinline__ void m3_gemv_phase(const Mega2Params& mp, const Mega2Phase& ph2, SM& sm, const M3Map& mapd, const M3Map& mapf, int cta, int rep_off,
+                                              int tid, unsigned g_idx, int par, unsigned in_tag, unsigned out_tag, int cur_pos, int* err,
+                                              unsigned long long* trace /* null or [8] */) {
+    const MegaPhase& ph = ph2.base;
+    const GemvParams& g = ph.g;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int buf = g_idx & 1;
+    const int d = mp.d_model;
+    const int K = g.K;
+    const bool isd = K == d;
+    const int K4 = K >> 2;
+    const bool grouped = isd ? mapd.grouped : mapf.grouped, in_group = isd ? mapd.in_group : mapf.in_group, active_warp = isd ? mapd.active_warp : mapf.active_warp;
+    const int G = isd ? mapd.G : mapf.G, rg = isd ? mapd.rg : mapf.rg, kq0 = isd ? mapd.kq0 : mapf.kq0, NS = isd ? mapd.NS : mapf.NS,
+              npw = isd ? mapd.npw : mapf.npw, wi = isd ? mapd.wi : mapf.wi;
+    // Every thread is past the barrier of the previous GEMV phase, i.e. nobody reads the other weight buffer any more: request the next
+    // GEMV's slice right away (a whole phase of lead).  Thread 416 has no columns in the grouped d_model mapping (K4 = 192).
+    if (tid == M2_THREADS - 96) prefetch_weights(ph.nx_W, ph.nx_ldw, ph.nx_N, ph.nx_K, sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, ph.nx_rpc);
+    int r0, r1;
+    cta_rows(g.N, cta, ph.rpc, r0, r1);
+    const int R = r1 - r0;
+    const bool ln = g.xmode == X_LAYERNORM;
+
+    // ---- epilogue operands, fetched NOW by the threads that will finish the rows (warps 14 / 15: thread 448 + e finishes decoder row e / R,
+    //      output row e % R), so that nothing but the sum itself is left behind the barrier ----
+    const int e = tid - (M2_THREADS - 64);
+    bool epi = false;
+    int eb = 0, elr = 0, act = 0, ll_nrep = 0;
+    float bias_v = 0.f, res_v = 0.f, alpha = 1.f;
+    ll_t* ll_out = nullptr;
+    long long ll_rs = 0;
+    float* plain = nullptr;
+    if (e >= 0 && e < R * NB) {
+        eb = (NB > 1 && e >= R) ? 1 : 0;
+        elr = e - eb * R;
+        epi = eb < g.B;
+        if (epi) {
+            const int n = r0 + elr;
+            const int si = (int)(g.nseg > 1 && n >= g.seg[1].n_begin) + (int)(g.nseg > 2 && n >= g.seg[2].n_begin);
+            const GemvSeg& sg = g.seg[si];
+            const int osel = ph2.out_sel[si], col = n - sg.n_begin;
+            if (g.bias) bias_v = __ldg(g.bias + n);
+            if (ph2.res_xraw) res_v = sm.xraw[eb * d + n];
+            act = sg.act; alpha = sg.alpha;
+            if (osel == LL_X || osel == LL_H) {
+                const long long width = osel == LL_H ? g.N : d;
+                ll_rs = osel == LL_H ? mp.ll.h_rep : mp.ll.x_rep;
+                ll_out = (osel == LL_H ? mp.ll.h : mp.ll.x) + (long long)eb * width + col;
+                ll_nrep = mp.ll.reps;
+            } else if (osel != LL_NONE) {
+                const long long width = osel == LL_K || osel == LL_V ? 2 * d : (osel == LL_LOGITS ? mp.V : d);
+                ll_out = ll_buf(mp.ll, osel) + (long long)eb * width + (osel == LL_V ? d : 0) + col;
+                ll_nrep = 1;
+            }
+            if (ph2.plain_out[si]) plain = sg.out + (long long)eb * sg.out_bs + (long long)cur_pos * sg.pos_stride + col;
+        }
+    }
+
+    // ---- input: polled straight into registers ----
+    float4 xv[NB][2];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { xv[b][0] = make_float4(0, 0, 0, 0); xv[b][1] = make_float4(0, 0, 0, 0); }
+    bool weights_waited = false;
+    if (R > 0) {
+        const ll_t* in = (ph2.in_sel == LL_H ? mp.ll.h + (long long)rep_off * mp.ll.h_rep
+                                             : (ph2.in_sel == LL_ATT ? mp.ll.att : mp.ll.x) + (long long)rep_off * mp.ll.x_rep);
+        if (ln || grouped) {
+            // one group polls (tid < K4), everybody else picks the values up from shared memory after the barrier
+            const bool poller = rg == 0 && kq0 < K4;
+            const bool has_col = in_group && kq0 < K4;
+            float4 lw = make_float4(0, 0, 0, 0), lb = lw;
+            if (ln && has_col) {
+                lw = __ldg(reinterpret_cast<const float4*>(g.ln_w) + kq0);
+                lb = __ldg(reinterpret_cast<const float4*>(g.ln_b) + kq0);
+            }
+            float4 raw[NB];
+            {
+                ll_t w[NB][4];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) { w[b][0] = w[b][1] = w[b][2] = w[b][3] = 0; }
+                if (poller) {
+                    long long spin = 0;
+                    bool first = true;
+                    while (true) {
+#pragma unroll
+                        for (int b = 0; b < NB; ++b)
+                            if (b < g.B) { const ll_t* src = in + (long long)b * K + kq0 * 4; ll_load2(src, w[b][0], w[b][1]); ll_load2(src + 2, w[b][2], w[b][3]); }
+                        if (first) { wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err); first = false; }      // overlaps the first round trip
+                        bool ok = true;
+#pragma unroll
+                        for (int b = 0; b < NB; ++b)
+                            if (b < g.B) ok = ok && ll_tag_ok4(w[b][0], w[b][1], w[b][2], w[b][3], in_tag);
+                        if (ok || !ll_spin_check(spin, err)) break;
+                    }
+                    weights_waited = true;
+                    if (trace && tid == 0) { trace[1] = (unsigned long long)clock64(); trace[7] = (unsigned long long)spin; }
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+                    raw[b] = (poller && b < g.B) ? make_float4(ll_val(w[b][0]), ll_val(w[b][1]), ll_val(w[b][2]), ll_val(w[b][3])) : make_float4(0, 0, 0, 0);
+            }
+            if (ln) {
+                // LayerNorm with the reduction structure of gemv_stage_x / m2_stage_ln (32-float4 chunks per warp, 8 chunk partials, fixed tree):
+                // the normalised activations carry the same bits as in the other token-loop drivers.
+                const int npl = (K4 + 31) >> 5;
+                const float inv = 1.0f / (float)K;
+                if (warp < npl) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const float sc = warp_sum((raw[b].x + raw[b].y) + (raw[b].z + raw[b].w));
+                        if (lane == 0) sm.ln_red[b * 8 + warp] = sc;
+                        if (poller) reinterpret_cast<float4*>(sm.xraw + b * K)[kq0] = raw[b];
+                    }
+                }
+                __syncthreads();
+                float mean[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) mean[b] = m3_tree8(sm.ln_red + b * 8) * inv;
+                if (warp < npl) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        float q = 0.f;
+                        if (poller && b < g.B) {
+                            const float a0 = raw[b].x - mean[b], a1 = raw[b].y - mean[b], a2 = raw[b].z - mean[b], a3 = raw[b].w - mean[b];
+                            q = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                        }
+                        q = warp_sum(q);
+                        if (lane == 0) sm.ln_red2[b * 8 + warp] = q;
+                    }
+                }
+                __syncthreads();
+                if (has_col) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        if (b < g.B) {
+                            const float rstd = rsqrtf(m3_tree8(sm.ln_red2 + b * 8) * inv + g.eps);
+                            const float4 v = poller ? raw[b] : reinterpret_cast<const float4*>(sm.xraw + b * K)[kq0];
+                            xv[b][0].x = (v.x - mean[b]) * rstd * lw.x + lb.x; xv[b][0].y = (v.y - mean[b]) * rstd * lw.y + lb.y;
+                            xv[b][0].z = (v.z - mean[b]) * rstd * lw.z + lb.z; xv[b][0].w = (v.w - mean[b]) * rstd * lw.w + lb.w;
+                        }
+                    }
+                }
+            } else {
+                if (poller) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) reinterpret_cast<float4*>(sm.u.xs + b * K)[kq0] = raw[b];
+                }
+                __syncthreads();
+                if (has_col) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) xv[b][0] = poller ? raw[b] : reinterpret_cast<const float4*>(sm.u.xs + b * K)[kq0];
+                }
+            }
+        } else {
+            // one group: every thread polls exactly the columns it multiplies, all loads in flight before the first tag check
+            ll_t w[NB][2][4];
+            bool on[NB][2];
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    on[b][s] = b < g.B && s < NS && kq0 + s * M2_THREADS < K4;
+                    w[b][s][0] = w[b][s][1] = w[b][s][2] = w[b][s][3] = 0;
+                }
+            long long spin = 0;
+            bool first = true;
+            while (true) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int s = 0; s < 2; ++s)
+                        if (on[b][s]) {
+                            const ll_t* src = in + (long long)b * K + (kq0 + s * M2_THREADS) * 4;
+                            ll_load2(src, w[b][s][0], w[b][s][1]);
+                            ll_load2(src + 2, w[b][s][2], w[b][s][3]);
+                        }
+                if (first) { wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err); first = false; }
+                bool ok = true;
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int s = 0; s < 2; ++s)
+                        if (on[b][s]) ok = ok && ll_tag_ok4(w[b][s][0], w[b][s][1], w[b][s][2], w[b][s][3], in_tag);
+                if (ok || !ll_spin_check(spin, err)) break;
+            }
+            weights_waited = true;
+            if (trace && tid == 0) { trace[1] = (unsigned long long)clock64(); trace[7] = (unsigned long long)spin; }
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+                    if (on[b][s]) xv[b][s] = make_float4(ll_val(w[b][s][0]), ll_val(w[b][s][1]), ll_val(w[b][s][2]), ll_val(w[b][s][3]));
+        }
+    }
+    if (trace && tid == 0) trace[2] = (unsigned long long)clock64();
+    if (!weights_waited) wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err);      // every thread observes the phase of the mbarrier it will wait on next time
+    if (trace && tid == 0) trace[3] = (unsigned long long)clock64();
+
+    // ---- multiply + reduce ----
+    if (R > 0 && active_warp && !(c_ll_debug & 4)) {
+        const int Pn = G == 1 ? R : (G == 2 ? (R + 1) >> 1 : (R + G - 1) / G);       // row slots per thread (host guarantees <= M3_SLOTS)
+        const float* wb = sm.wbuf[buf];
+        int kqc[2];
+        kqc[0] = kq0 < K4 ? kq0 : 0;
+        kqc[1] = kq0 + M2_THREADS < K4 ? kq0 + M2_THREADS : 0;
+        float* red0 = &sm.red[par][0][0][0];
+        float* red1 = &sm.red[par][NB - 1][0][0];
+#pragma unroll 1
+        for (int p0 = 0; p0 < Pn; p0 += 8) {
+            if (NS == 1) m3_pass<NB, 1>(wb, K, R, G, rg, p0, kqc, xv, red0, red1, wi, lane);
+            else         m3_pass<NB, 2>(wb, K, R, G, rg, p0, kqc, xv, red0, red1, wi, lane);
+        }
+    }
+    if (trace && tid == 0) trace[4] = (unsigned long long)clock64();
+    asm volatile("cp.async.wait_all;" ::: "memory");   // next phase's descriptor (issued at the top of the phase loop)
+    __syncthreads();
+    if (trace && tid == 0) trace[5] = (unsigned long long)clock64();
+
+    // ---- epilogue: sum of the warp partials (fixed tree over 16 slots, unused ones read as zero), bias / activation / residual, tagged store ----
+    if (epi) {
+        const float4* r4 = reinterpret_cast<const float4*>(&sm.red[par][eb][elr][0]);
+        float4 q[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = r4[i];
+        float t[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w, q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i] = i < npw ? t[i] : 0.f;
+        float v = (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) + (((t[8] + t[9]) + (t[10] + t[11])) + ((t[12] + t[13]) + (t[14] + t[15])));
+        v += bias_v;
+        v = apply_act(v, act) * alpha;
+        v += res_v;
+        for (int rep = 0; rep < ll_nrep; ++rep) ll_store(ll_out + rep * ll_rs, v, out_tag);
+        if (plain) {
+            *plain = v;
+            __threadfence();                           // K/V cache rows are read by LATER tokens through plain loads (see the header comment)
+        }
+        if (trace && e == 0) trace[6] = (unsigned long long)clock64();
+    }
+}
+
 // TRACE = true is a separate instantiation for tools/mega2_trace.py: CTAs 0, 1, 100 and 140 stamp clock64 at four points of every phase
 // of token `trace_step` (phase start, input staged, weights landed, rows / units done); the production kernel carries no stamp code.
-template <int NB, bool TRACE>
+// MODE 0: GEMV phases stage the activation in shared memory and give every warp whole output rows (the barrier kernel's gemv_dot).
+// MODE 1: K-split GEMV phases (m3_*): every thread polls ITS k-slice of the activation straight into registers, multiplies it with
+//         its slice of every weight row the CTA owns, and the CTA reduces the partial sums (warp butterfly + 16 warp partials).
+template <int NB, bool TRACE, int MODE>
 __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Params mp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     M2Smem& sm = *reinterpret_cast<M2Smem*>(smem_raw);
@@ -414,6 +753,7 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     m2_clear_ln_red(sm.ln_red, tid);
+    m2_clear_ln_red(sm.ln_red2, tid);
     __syncthreads();
     unsigned int g_idx = 0;          // running index of GEMV phases (selects weight buffer + mbarrier parity)
     if (tid == 0) {
@@ -439,6 +779,8 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
     __syncthreads();
     int cur = 0;
     AttnRegs<M2_WARPS> areg;
+    const M3Map mapd = m3_make_map(mp.d_model, tid), mapf = m3_make_map(mp.ffn_dim > 0 ? mp.ffn_dim : mp.d_model, tid);
+    const int rep_off = cta % mp.ll.reps;
 
     for (int step = 0; step < mp.max_steps; ++step) {
         if (tid == 0) {      // token header: written by the selection phase of the previous token (or the prologue above)
@@ -454,7 +796,8 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
         if (fin || e) break;
         const int tslot = cta == 0 ? 0 : (cta == 1 ? 1 : (cta == 100 ? 2 : (cta == 140 ? 3 : -1)));
         const bool tracing = TRACE && mp.trace != nullptr && step == mp.trace_step && tslot >= 0 && tid == 0;
-#define M2_TRACE(slot) do { if (tracing) mp.trace[((long long)tslot * mp.n_phases + pi) * 4 + (slot)] = (unsigned long long)clock64(); } while (0)
+#define M2_TRACE(slot) do { if (tracing) { if (MODE == 1) { if (tslot < 2) mp.trace[((long long)tslot * mp.n_phases + pi) * 8 + ((slot) == 3 ? 5 : (slot))] = (unsigned long long)clock64(); } \
+                                           else mp.trace[((long long)tslot * mp.n_phases + pi) * 4 + (slot)] = (unsigned long long)clock64(); } } while (0)
         for (int pi = 0; pi < mp.n_phases; ++pi) {
             M2_TRACE(0);
             const Mega2Phase& ph2 = sm.phase[cur];
@@ -463,11 +806,23 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
             const unsigned out_tag = ll_tag(step, pi);
             // next phase's descriptor: global -> shared asynchronously, drained before the end-of-phase CTA barrier
             constexpr int DESC_WORDS = (int)(sizeof(Mega2Phase) / 4);
-            for (int i = tid; i < DESC_WORDS; i += M2_THREADS) {
+            const int nxt = cur == 2 ? 0 : cur + 1;
+            // (K-split mode: by warps 12..15, which hold no columns of the d_model-wide inputs, so the pollers start polling at once)
+            for (int i = MODE == 1 ? tid - 384 : tid; i >= 0 && i < DESC_WORDS; i += MODE == 1 ? 128 : M2_THREADS) {
                 const int* src = reinterpret_cast<const int*>(&mp.phases[pi + 1 < mp.n_phases ? pi + 1 : 0]) + i;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(reinterpret_cast<int*>(&sm.phase[cur ^ 1]) + i)), "l"(src) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(reinterpret_cast<int*>(&sm.phase[nxt]) + i)), "l"(src) : "memory");
             }
-            if (ph.kind == 0) {
+            if (ph.kind == 0 && MODE == 1) {
+                // finer timeline than MODE 0: CTAs 0 and 1 only, 8 stamps per phase (0 start, 1 polled, 2 input ready, 3 weights landed,
+                // 4 partial sums written, 5 past the barrier, 6 epilogue of output row 0 stored, 7 = failed polls of thread 0)
+                unsigned long long* tr = nullptr;
+                if (TRACE && mp.trace != nullptr && step == mp.trace_step && cta < 2) {
+                    tr = mp.trace + ((long long)cta * mp.n_phases + pi) * 8;
+                    if (tid == 0) tr[0] = (unsigned long long)clock64();
+                }
+                m3_gemv_phase<NB>(mp, ph2, sm, mapd, mapf, cta, rep_off, tid, g_idx, pi & 1, in_tag, out_tag, cur_pos, err, tr);
+                ++g_idx;
+            } else if (ph.kind == 0) {
                 const GemvParams& g = ph.g;
                 const int buf = g_idx & 1;
                 int r0, r1;
@@ -553,10 +908,12 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
                     sample_body(sm.sample_params, cta, sm.u.sample);
                 }
             }
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncthreads();                              // xs / attention scratch free for the next phase; the next descriptor has landed
-            M2_TRACE(3);
-            cur ^= 1;
+            if (!(ph.kind == 0 && MODE == 1)) {           // (the K-split GEMV phase ends with its own barrier, before its epilogue)
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncthreads();                          // xs / attention scratch free for the next phase; the next descriptor has landed
+                M2_TRACE(3);
+            }
+            cur = nxt;
         }
     }
 #undef M2_TRACE
@@ -572,30 +929,51 @@ int mega2_set_poll_sleep(int ns) {
     MB_CUDA_CHECK(cudaMemcpyToSymbol(c_ll_sleep_ns, &ns, sizeof(int)));
     return 0;
 }
+int mega2_set_debug(int bits) {
+    MB_CUDA_CHECK(cudaMemcpyToSymbol(c_ll_debug, &bits, sizeof(int)));
+    return 0;
+}
+
+template <int NB, bool TRACE, int MODE>
+static const void* m2_configure() {
+    const void* fn = (const void*)decode_megakernel_ll<NB, TRACE, MODE>;
+    static bool done = false;
+    if (!done) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()) != cudaSuccess) return nullptr;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, M2_THREADS, mega2_smem_bytes()) != cudaSuccess || per_sm < 1) return nullptr;
+        done = true;
+    }
+    return fn;
+}
 
 int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
-        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
-        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
-        MB_CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel_ll<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()));
-        int per_sm = 0;
-        MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel_ll<2, true>, M2_THREADS, mega2_smem_bytes()));
-        MB_REQUIRE(per_sm >= 1, "dataflow megakernel does not fit on an SM");
-        configured = true;
-    }
     MB_REQUIRE(mp.rows >= 1 && mp.rows <= M2_NB_MAX, "megakernel handles 1 or 2 decoder rows");
     MB_REQUIRE(mp.n_phases <= 126, "tag layout holds at most 126 phases per token");
     MB_REQUIRE(mp.d_model <= 1024, "residual scratch holds d_model <= 1024");
+    const bool tr = mp.trace != nullptr, one = mp.rows == 1;
+    const void* fn = nullptr;
+    if (mp.gemv_mode == 1) {
+        fn = tr ? (one ? m2_configure<1, true, 1>() : m2_configure<2, true, 1>()) : (one ? m2_configure<1, false, 1>() : m2_configure<2, false, 1>());
+    } else {
+        fn = tr ? (one ? m2_configure<1, true, 0>() : m2_configure<2, true, 0>()) : (one ? m2_configure<1, false, 0>() : m2_configure<2, false, 0>());
+    }
+    MB_REQUIRE(fn != nullptr, "dataflow megakernel does not fit on an SM");
     Mega2Params p = mp;
     void* args[] = {&p};
-    const void* fn = mp.trace ? (mp.rows == 1 ? (const void*)decode_megakernel_ll<1, true> : (const void*)decode_megakernel_ll<2, true>)
-                              : (mp.rows == 1 ? (const void*)decode_megakernel_ll<1, false> : (const void*)decode_megakernel_ll<2, false>);
     // Cooperative launch for its co-residency guarantee: every CTA polls values that other CTAs produce, so all of them must be resident.
     MB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(M2_THREADS), args, mega2_smem_bytes(), stream));
     ++g_launch_count;
     return 0;
+}
+
+// Limits of the K-split GEMV mapping for one phase (checked on the host when the phase table is built)
+bool mega2_ksplit_ok(int N, int K, int rows, int grid) {
+    const int K4 = K >> 2, rpc = (N + grid - 1) / grid;
+    if ((K & 3) || K4 > 2 * M2_THREADS) return false;
+    const bool grouped = (K4 & 31) == 0 && K4 <= 256;
+    const int G = grouped ? M2_THREADS / K4 : 1;
+    return (rpc + G - 1) / G <= M3_SLOTS && rpc <= M3_ROWS && rpc * rows <= 64;
 }
 
 }  // namespace mb200

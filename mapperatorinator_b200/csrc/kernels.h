@@ -281,11 +281,14 @@ struct Mega2Params {
     int max_steps;
     const int* row_slot;
     const float* x_in;                            // [rows][d] plain residual stream left by the prefill's selection kernel
-    int rows, d_model, V;
+    int rows, d_model, V, ffn_dim;
     unsigned long long* trace; int trace_step;    // optional [4 CTAs][n_phases][4] clock64 stamps (tools/mega2_trace.py)
+    int gemv_mode;                                // 0 row-per-warp GEMV phases (shared-memory staging), 1 K-split GEMV phases (decode_mega2.cu, m3_*)
 };
 size_t mega2_smem_bytes();
 int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream);
+bool mega2_ksplit_ok(int N, int K, int rows, int grid);   // does one GEMV phase fit the K-split thread mapping?
+int mega2_set_debug(int bits);                    // diagnostics (decode_device.cuh, c_ll_debug)
 int mega2_set_poll_sleep(int ns);                 // tuning: nanoseconds to back off after a failed poll (0 = spin)
 
 // one-time per call: scan the prompt for the MonotonicTimeShift state (logit_processors.py:149-166)

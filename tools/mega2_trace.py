@@ -22,7 +22,7 @@ layout = TokenLayout.from_json(os.path.join(ROOT, "tests", "golden", "tokenizer_
 model = B200Mapperatorinator(cfg, init_model_state_dict(cfg, 0), max_windows=2, max_batch=2)
 windows, _, _ = bench.segment(bench.synth_song(0, 20.0), cfg)
 model.engine.encode(windows[:2].cuda(), 0)
-model.engine.set_option("mega", 2)
+model.engine.set_option("mega", int(os.environ.get("MB200_MEGA", "3")))
 model.engine.set_option("mega_trace", 1)
 if os.environ.get("MB200_LL_REPS"):
     model.engine.set_option("ll_reps", int(os.environ["MB200_LL_REPS"]))
