@@ -265,7 +265,7 @@ def main() -> None:
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("MB200_PDL", "0")))
     ap.add_argument("--windows", type=int, default=0, help="debug: truncate the song to this many windows")
     ap.add_argument("--tc", type=int, default=int(os.environ.get("MB200_TC", "1")), help="1 = tcgen05 3xTF32 GEMMs where eligible, 0 = fp32 SIMT GEMM everywhere")
-    ap.add_argument("--mega", type=int, default=3, help="3 = dataflow token-loop megakernel with K-split GEMV phases (default), 2 = dataflow with row-per-warp GEMV phases, 1 = grid-barrier megakernel, 0 = CUDA-graph replay per token")
+    ap.add_argument("--mega", type=int, default=2, help="2 = dataflow token-loop megakernel (default), 1 = grid-barrier megakernel, 0 = CUDA-graph replay per token")
     ap.add_argument("--cpu-threads", type=int, default=int(os.environ.get("MB200_CPU_THREADS", "0")),
                     help="torch threads of the CPU arm (0 = min(cores, 16): measured best on the GPU box; 32+ threads slow a batch-1 decoder down)")
     args = ap.parse_args()

@@ -642,6 +642,232 @@ struct SampleSmem {
     int wi[SAMPLE_THREADS / 32];
 };
 
+
+// ---- register-resident greedy chain (dataflow megakernel) ------------------------------------------------------------------------------
+// sample_body walks the vocabulary through shared memory once per processor (rolled loops, three CTA barriers per reduction): 15 us
+// per token on ONE CTA while 147 wait for the next token's embedding.  For greedy selection every stage is elementwise or a reduction,
+// so the thread's V / NT scores can stay in registers from the poll to the argmax: one pass, three fused reductions (two maxima; four
+// sums; the argmax), each one warp shuffle tree + one barrier + one shuffle tree in EVERY warp (no broadcast barrier).  The per-thread
+// visiting order (v = tid, tid + NT, ...) and the two-level shuffle trees are those of sample_body / block_reduce, so the scores carry
+// the same bits as the shared-memory chain with the same NT.
+template <int NT, int N>
+static __device__ __forceinline__ void block_reduce_fused(float (&v)[N], bool is_max, float* region /* >= N * 32 floats, alternate between calls */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = is_max ? warp_max(v[k]) : warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) region[k * 32 + warp] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        float t = lane < NT / 32 ? region[k * 32 + lane] : (is_max ? -INFINITY : 0.f);
+        v[k] = is_max ? warp_max(t) : warp_sum(t);
+    }
+}
+
+// (0)+(1) of the chain for the dataflow megakernel: tagged logits -> CFG mix -> min_new_tokens EOS suppression -> s[v] (per-thread slots
+// v = tid + j * NT).
+template <int NT>
+static __device__ __forceinline__ void sample_poll_ll(const SampleParams& p, int b, float* s, bool suppress_eos) {
+    constexpr int PER = VMAX / NT;
+    const int tid = threadIdx.x;
+    const SampleConfig& c = *p.cfg;
+    const int V = c.V, B = c.B;
+    const unsigned in_tag = p.ll_in_tag;
+    const unsigned char* __restrict__ vfl = p.vflags;
+    const bool use_cfg = c.use_cfg != 0;
+    const float cfg_scale = c.cfg_scale;
+    // Polled in rounds of 8 pairs per thread (all 8 in flight before the first tag check); the conditional half of a CFG pair waits in
+    // s[] itself for the unconditional one.
+    {
+        constexpr int CH = 8;
+        for (int half = 0; half < (use_cfg ? 2 : 1); ++half) {
+            const ll_t* src = p.ll_logits + (long long)(half * B + b) * V;
+#pragma unroll 1
+            for (int j0 = 0; j0 < PER; j0 += CH) {
+                ll_t w[CH];
+                long long spin = 0;
+                while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        const int v = tid + (j0 + j) * NT;
+                        if (v < V) asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w[j]) : "l"(src + v) : "memory");
+                    }
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        const int v = tid + (j0 + j) * NT;
+                        if (v < V) ok = ok && (unsigned)(w[j] >> 32) == in_tag;
+                    }
+                    if (ok || !ll_spin_check(spin, p.ll_err)) break;
+                    __nanosleep(96);      // one CTA spinning on 29 KB of lines that 147 CTAs are storing into: back off so the stores get through
+                }
+                // (flags first, all at once: a load behind a conditional cannot be moved above the previous element's store by the compiler,
+                //  and eight dependent L2 round trips cost 3 us here)
+                unsigned char fl[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int v = tid + (j0 + j) * NT;
+                    fl[j] = (suppress_eos && v < V) ? __ldg(vfl + v) : (unsigned char)0;
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int v = tid + (j0 + j) * NT;
+                    if (v < V) {
+                        const float xv = __uint_as_float((unsigned)w[j]);
+                        if (use_cfg && half == 0) s[v] = xv;                   // first half = "conditional" in HF's processor
+                        else {
+                            const float y = use_cfg ? xv + (s[v] - xv) * cfg_scale : xv;
+                            s[v] = (fl[j] & VF_EOS) ? -INFINITY : y;
+                        }
+                    }
+                }
+                if (p.trace && tid == 0 && j0 == 0) { p.trace[7] = (unsigned long long)clock64(); p.trace[10] = (unsigned long long)spin; }
+            }
+        }
+    }
+}
+
+template <int NT>
+static __device__ __forceinline__ int sample_greedy_regs(const SampleParams& p, int b, SampleSmem& sm, int L, int st_step, int st_has_last, bool suppress_eos) {
+    constexpr int PER = VMAX / NT;
+    const int tid = threadIdx.x;
+    const SampleConfig& c = *p.cfg;
+    const int V = c.V, B = c.B;
+    float* regions = reinterpret_cast<float*>(sm.sidx);            // the sort's index array is idle on the greedy path: 2 x 4 x 32 floats of scratch
+    // Every thread only ever touches ITS OWN scores (v = tid + j * NT): s[] is per-thread scratch here, so no barrier is needed between
+    // the passes — only inside the reductions.  (Registers instead of s[] made this function so register-hungry that the calling
+    // megakernel spilled in its per-layer phases: +10 % per token.)
+    float* s = sm.s;
+    sample_poll_ll<NT>(p, b, s, suppress_eos);
+    if (p.trace && tid == 0) p.trace[1] = (unsigned long long)clock64();
+    // (2) MonotonicTimeShift, (3) TimeshiftBias, (4) temperature (decided on batch row 0)
+    const int lts = p.last_ts[b];
+    float temp = c.temperature;
+    if (c.types_first) {
+        for (int i = 0; i < c.n_cond; ++i) {
+            const int off = c.cond_offset[i];
+            if (L >= off) {
+                long long t0 = __ldcg(p.ids + (L - off));   // row 0
+                if (t0 >= 0 && (p.vflags[t0] & c.cond_flag[i])) { temp = c.cond_temp[i]; break; }
+            }
+        }
+    }
+    const bool lb_plain = c.lookback_on && !c.types_first;
+    const bool lb_scores = c.lookback_on && c.types_first;
+    float* ls_cur = p.last_scores + ((long long)(st_step & 1) * B + b) * V;
+    const float* ls_prev = p.last_scores + ((long long)((st_step + 1) & 1) * B + b) * V;
+    bool lb_apply = false;
+    if (lb_scores) {
+        const long long last_tok = L > 0 ? __ldcg(p.ids + (long long)b * c.ids_ld + (L - 1)) : -1;
+        lb_apply = st_has_last && last_tok >= 0 && (p.vflags[last_tok] & VF_TIMED);
+    }
+    // The passes below run in batches of 4 elements with every load of a batch issued before its first store: the compiler must assume
+    // that s[], the two score buffers and the flags alias, so a load written after a store stays behind it (one L2 round trip per element).
+    constexpr int BT = 4;
+    const int ts_start = c.ts_start, ts_end = c.ts_end, lb_start = c.lookback_start, lb_end = c.lookback_end;
+    const float ts_bias = c.timeshift_bias;
+    const unsigned char* __restrict__ vfl = p.vflags;
+    float mm[2] = {-INFINITY, -INFINITY};                          // max of the previous step's scores, max of this step's
+#pragma unroll 1
+    for (int v0 = tid; v0 < V; v0 += BT * NT) {
+        float xv[BT], lp[BT];
+#pragma unroll
+        for (int k = 0; k < BT; ++k) {
+            const int v = v0 + k * NT;
+            xv[k] = v < V ? s[v] : -INFINITY;
+            lp[k] = (lb_apply && v < V) ? __ldcg(ls_prev + v) : -INFINITY;
+        }
+#pragma unroll
+        for (int k = 0; k < BT; ++k) {
+            const int v = v0 + k * NT;
+            float x = xv[k];
+            if (v >= ts_start && v < ts_end) {
+                if (lts >= 0 && v < ts_start + lts) x = -INFINITY;
+                if (ts_bias != 0.f) x += ts_bias;
+            }
+            x = x / temp;
+            if (lb_plain && v >= lb_start && v < lb_end) x = -INFINITY;
+            xv[k] = x;
+            if (lb_apply && v < V) { mm[0] = fmaxf(mm[0], lp[k]); mm[1] = fmaxf(mm[1], x); }
+        }
+#pragma unroll
+        for (int k = 0; k < BT; ++k) {
+            const int v = v0 + k * NT;
+            if (v < V) {
+                s[v] = xv[k];
+                if (lb_scores) ls_cur[v] = xv[k];
+            }
+        }
+    }
+    // (5) LookbackBias with the previous step's scores
+    if (lb_apply) {
+        block_reduce_fused<NT, 2>(mm, true, regions);
+        const float m_last = mm[0], m_cur = mm[1];
+        float zz[4] = {0.f, 0.f, 0.f, 0.f};                        // z_last, z_cur, e_last, o_cur
+#pragma unroll 1
+        for (int v0 = tid; v0 < V; v0 += BT * NT) {
+            float xv[BT], lp[BT];
+            unsigned char fl[BT];
+#pragma unroll
+            for (int k = 0; k < BT; ++k) {
+                const int v = v0 + k * NT;
+                xv[k] = v < V ? s[v] : -INFINITY;
+                lp[k] = v < V ? __ldcg(ls_prev + v) : -INFINITY;
+                fl[k] = v < V ? __ldg(vfl + v) : (unsigned char)0;
+            }
+#pragma unroll
+            for (int k = 0; k < BT; ++k) {                         // (element order v0, v0 + NT, ... : the accumulation order of sample_body)
+                const int v = v0 + k * NT;
+                if (v < V) {
+                    const float pl = expf(lp[k] - m_last);
+                    const float pc = expf(xv[k] - m_cur);
+                    zz[0] += pl; zz[1] += pc;
+                    if (fl[k] & VF_LB_EOS) zz[2] += pl;
+                    if (!(v >= lb_start && v < lb_end)) zz[3] += pc;
+                }
+            }
+        }
+        block_reduce_fused<NT, 4>(zz, false, regions + 4 * 32);
+        const float prob_eos = zz[2] / zz[0];
+        const float prob_event = 1.f - prob_eos;
+        const float sc = 1.f / ((zz[3] / zz[1]) * prob_event + prob_eos);
+        const float extra = fminf(fmaxf((sc - 1.f) * prob_eos / prob_event, 0.f), 1.f);
+#pragma unroll 4
+        for (int v = tid; v < V; v += NT) {
+            float pr;
+            if (v == lb_start) pr = extra;
+            else if (v >= lb_start && v < lb_end) pr = 0.f;
+            else pr = (expf(s[v] - m_cur) / zz[1]) * sc;
+            s[v] = logf(pr);
+        }
+    }
+    if (p.trace && tid == 0) p.trace[2] = (unsigned long long)clock64();
+    // (6) argmax, first index on ties (torch.argmax)
+    float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 4
+    for (int v = tid; v < V; v += NT) {
+        const float xv = s[v];
+        if (xv > best || (xv == best && v < bi)) { best = xv; bi = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if ((tid & 31) == 0) { sm.wb[tid >> 5] = best; sm.wi[tid >> 5] = bi; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+        const float ob = sm.wb[w]; const int oi = sm.wi[w];
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    return bi == 0x7fffffff ? 0 : bi;
+}
+
 // The whole logits-processor chain + token selection + append for batch row b (one CTA of NT threads).
 // Deliberately NOT inlined and with rolled vocabulary loops: it runs once per token on one CTA; inlined and unrolled it was 70 KB of
 // the megakernel's 130 KB of code.  (A cold/warm re-run experiment later showed the per-layer phases are NOT instruction-fetch bound,
@@ -663,43 +889,15 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
     long long* ids_row = p.ids + (long long)b * c.ids_ld;
     const bool suppress_eos = st_min_new > 0 && (L - st_prompt_len) < st_min_new;
 
+    if (p.trace && tid == 0) p.trace[6] = (unsigned long long)clock64();
+    int chosen = 0;
+    const bool fast_greedy = p.ll_logits != nullptr && !c.do_sample && p.dbg_scores == nullptr && V <= VMAX;
+    if (fast_greedy) {
+        chosen = sample_greedy_regs<NT>(p, b, sm, L, st_step, st_has_last, suppress_eos);
+    } else {
     // (0)+(1): min_new_tokens EOS suppression, then classifier-free guidance on raw logits
     if (p.ll_logits) {
-        // dataflow megakernel: logits arrive as tagged pairs; all of a thread's pairs are requested before the first tag is examined
-        constexpr int PER = VMAX / NT;
-        float cond[PER];
-        for (int half = 0; half < (c.use_cfg ? 2 : 1); ++half) {      // conditional rows, then (CFG only) the unconditional rows
-            ll_t w[PER];
-            const ll_t* src = p.ll_logits + (long long)(half * B + b) * V;
-            long long spin = 0;
-            while (true) {
-                bool ok = true;
-#pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    const int v = tid + j * NT;
-                    if (v < V) asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w[j]) : "l"(src + v) : "memory");
-                }
-#pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    const int v = tid + j * NT;
-                    if (v < V) ok = ok && (unsigned)(w[j] >> 32) == p.ll_in_tag;
-                }
-                if (ok || !ll_spin_check(spin, p.ll_err)) break;
-            }
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const int v = tid + j * NT;
-                if (v < V) {
-                    const float x = __uint_as_float((unsigned)w[j]);
-                    if (half == 0) cond[j] = x;                            // first half = "conditional" in HF's processor
-                    if (half == 1 || !c.use_cfg) {
-                        const bool eos = (p.vflags[v] & VF_EOS) != 0;
-                        const float y = c.use_cfg ? x + (cond[j] - x) * c.cfg_scale : x;
-                        s[v] = (suppress_eos && eos) ? -INFINITY : y;
-                    }
-                }
-            }
-        }
+        sample_poll_ll<NT>(p, b, s, suppress_eos);
     } else {
     _Pragma("unroll 1") for (int v = tid; v < V; v += NT) {
         float x;
@@ -783,7 +981,6 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
     }
 
     // (6)-(7) selection
-    int chosen = 0;
     if (!c.do_sample) {
         if (p.dbg_scores) { _Pragma("unroll 1") for (int v = tid; v < V; v += NT) p.dbg_scores[(long long)b * V + v] = s[v]; }
         // argmax, first index on ties (torch.argmax)
@@ -917,6 +1114,9 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         chosen = sm.chosen_sh;
     }
 
+    }   // !fast_greedy
+
+    if (p.trace && tid == 0) p.trace[3] = (unsigned long long)clock64();
     // (8) finished rows emit pad; append; EOS test; state updates; next-step embedding
     const bool was_finished = p.finished[b] != 0;
     const long long tok = was_finished ? (long long)c.pad_id : (long long)chosen;
@@ -953,21 +1153,25 @@ static __device__ __noinline__ void sample_body(const SampleParams& p, int b, Sa
         }
     }
     __syncthreads();
+    if (p.trace && tid == 0) p.trace[4] = (unsigned long long)clock64();
     if (tid == 0) {
-        __threadfence();
+        // Last row to arrive publishes the next token's header.  Dataflow megakernel: the tagged header goes out FIRST (its consumers
+        // synchronise on the tag, not on the fences); the plain state for the host / the per-phase kernels follows.
+        if (B > 1) __threadfence();                    // this row's n_finished update before its ticket
         if (atomicAdd(&st->ticket, 1) == B - 1) {
-            st->ticket = 0;
-            st->cur_len = L + 1;
-            st->step = st_step + 1;
-            st->has_last_scores = 1;
             const int fin_all = (ld_state(&st->n_finished) >= B || L + 1 >= st_max_length) ? 1 : 0;
-            if (fin_all) st->all_finished = 1;
-            __threadfence();
             if (p.ll_hdr) {        // token header of the dataflow megakernel: next cur_len, all-finished flag
                 ll_store(p.ll_hdr + 0, __int_as_float(L + 1), p.ll_out_tag);
                 ll_store(p.ll_hdr + 1, __int_as_float(fin_all), p.ll_out_tag);
             }
+            st->ticket = 0;
+            st->cur_len = L + 1;
+            st->step = st_step + 1;
+            st->has_last_scores = 1;
+            if (fin_all) st->all_finished = 1;
+            __threadfence();
         }
+        if (p.trace) p.trace[5] = (unsigned long long)clock64();
     }
 }
 

@@ -26,13 +26,14 @@ namespace mb200 {
 
 namespace {
 
-constexpr int M2_THREADS = SAMPLE_THREADS;              // 512
+constexpr int M2_THREADS = 256;                         // 8 warps, 255 registers per thread: the phases are chains of dependent latencies, not throughput
 constexpr int M2_WARPS = M2_THREADS / 32;
 constexpr int M2_NB_MAX = 2;
-constexpr int M2_XS_FLOATS = M2_NB_MAX * 3072;
+constexpr int M2_XS_FLOATS = M2_NB_MAX * 1024;
 constexpr int M2_XRAW_FLOATS = M2_NB_MAX * 1024;
 constexpr int M2_PART = 66;                             // pairs per split partial: o[64], m, l
-constexpr int M3_SLOTS = 16;                            // K-split GEMV: output rows per thread (row slots), two passes of 8
+constexpr int M3_SLOTS = 32;                            // K-split GEMV: output rows per thread (row slots), passes of 8
+constexpr int M3_NS = 4;                                // K-split GEMV: float4 columns per thread (K <= 4 * 4 * 256)
 constexpr int M3_ROWS = 32;                             // K-split GEMV: output rows per CTA and phase
 
 struct __align__(16) M2Smem {
@@ -51,6 +52,8 @@ struct __align__(16) M2Smem {
     __align__(16) float red[2][M2_NB_MAX][M3_ROWS][M2_WARPS];     // [phase parity][decoder row][output row of this CTA][warp of the row's group]
     float ln_red2[32];
     unsigned long long mbar[2];
+    unsigned long long wfree[2];                // weight buffer b has been read by every warp (arrive count = warps): the next bulk copy may overwrite it
+    __align__(16) float xrw[2][M2_NB_MAX * 1024]; // row-per-warp GEMV phases: the (normalised) activation, double-buffered by phase parity
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -109,54 +112,6 @@ __device__ __forceinline__ ll_t* ll_buf(const MegaLL& ll, int sel) {
     }
 }
 
-// ---- activation staging ---------------------------------------------------------------------------------------------------------
-// LayerNorm prologue over the tagged residual stream: the reduction structure of gemv_stage_x (chunk of 32 float4 per warp, 8 chunk
-// partials per row reduced by a fixed tree), operands polled instead of loaded; the raw values are kept in `xraw` (this CTA adds them
-// back as the residual of the rows it owns two phases later, so the residual needs no second trip through L2).
-template <int NB>
-__device__ __forceinline__ void m2_stage_ln(const GemvParams& p, const ll_t* ll_in, unsigned tag, float* xs, float* xraw, float* red, int tid, int* err) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int K = p.K, K4 = K >> 2;
-    constexpr int RG = M2_WARPS / 8;                   // rows staged per round (16 warps: 2)
-    const float inv = 1.0f / (float)K;
-    for (int g0 = 0; g0 < NB; g0 += RG) {
-        const int rl = warp >> 3, bb = g0 + rl, c0 = warp & 7;
-        const bool row_ok = bb < NB && bb < p.B;
-        const int idx = c0 * 32 + lane;
-        const bool ok = row_ok && idx < K4;
-        float4 v = make_float4(0, 0, 0, 0), lw = v, lb = v;
-        if (ok) {
-            lw = __ldg(reinterpret_cast<const float4*>(p.ln_w) + idx);
-            lb = __ldg(reinterpret_cast<const float4*>(p.ln_b) + idx);
-            v = ll_wait4(ll_in + (long long)bb * K + idx * 4, tag, err);
-            reinterpret_cast<float4*>(xraw + bb * K)[idx] = v;
-        }
-        const float sc = warp_sum((v.x + v.y) + (v.z + v.w));
-        if (lane == 0) red[rl * 8 + c0] = sc;
-        __syncthreads();
-        const float* r = red + rl * 8;
-        const float mean = (((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))) * inv;
-        float q = 0.f;
-        if (ok) {
-            const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-            q = (a * a + b * b) + (c * c + d * d);
-        }
-        q = warp_sum(q);
-        if (lane == 0) red[RG * 8 + rl * 8 + c0] = q;
-        __syncthreads();
-        if (bb < NB && idx < K4) {
-            const float* r2 = red + RG * 8 + rl * 8;
-            const float rstd = rsqrtf((((r2[0] + r2[1]) + (r2[2] + r2[3])) + ((r2[4] + r2[5]) + (r2[6] + r2[7]))) * inv + p.eps);
-            float4 o = make_float4(0, 0, 0, 0);
-            if (row_ok) {
-                o.x = (v.x - mean) * rstd * lw.x + lb.x; o.y = (v.y - mean) * rstd * lw.y + lb.y;
-                o.z = (v.z - mean) * rstd * lw.z + lb.z; o.w = (v.w - mean) * rstd * lw.w + lb.w;
-            }
-            reinterpret_cast<float4*>(xs + bb * K)[idx] = o;
-        }
-    }
-}
-
 // chunk partials of warps that hold no chunk (c0 >= K4 / 32) must read as zero: the fixed tree always adds eight of them
 __device__ __forceinline__ void m2_clear_ln_red(float* red, int tid) {
     if (tid < 32) red[tid] = 0.f;
@@ -169,50 +124,13 @@ __device__ __forceinline__ bool ll_tag_ok4(ll_t a, ll_t b, ll_t c, ll_t d, unsig
 }
 __device__ __forceinline__ float ll_val(ll_t a) { return __uint_as_float((unsigned)a); }
 
-template <int NB>
-__device__ __forceinline__ void m2_stage_plain(const GemvParams& p, const ll_t* ll_in, unsigned tag, float* xs, int tid, int* err) {
-    const int K4 = p.K >> 2;
-    constexpr int U = 3;                               // float4 per thread per batch (K = 3072: 1.5 per decoder row)
-    for (int e0 = tid; e0 < NB * K4; e0 += U * M2_THREADS) {
-        ll_t w[U][4];
-        bool on[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = e0 + u * M2_THREADS, bb = e / K4;
-            on[u] = e < NB * K4 && bb < p.B;
-        }
-        long long spin = 0;
-        while (true) {
-            bool ok = true;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (on[u]) {
-                    const int e = e0 + u * M2_THREADS, bb = e / K4, c = e - bb * K4;
-                    const ll_t* src = ll_in + (long long)bb * p.K + c * 4;
-                    ll_load2(src, w[u][0], w[u][1]);
-                    ll_load2(src + 2, w[u][2], w[u][3]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (on[u]) ok = ok && ll_tag_ok4(w[u][0], w[u][1], w[u][2], w[u][3], tag);
-            if (ok || !ll_spin_check(spin, err)) break;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = e0 + u * M2_THREADS;
-            if (e < NB * K4) reinterpret_cast<float4*>(xs)[e] = on[u] ? make_float4(ll_val(w[u][0]), ll_val(w[u][1]), ll_val(w[u][2]), ll_val(w[u][3])) : make_float4(0, 0, 0, 0);
-        }
-    }
-}
-
 // ---- attention unit -------------------------------------------------------------------------------------------------------------
 // (split s, head h, row r) exactly like decode_attention_body<16>: the same score chains, the same per-warp softmax statistics, the same
 // four PV accumulation chains — only the operand sources differ: q and the newest K/V row are polled from the exchange buffers, the
 // result leaves as tagged pairs (merged heads when one split covers the context, else a split partial that the split-0 CTA merges).
 __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const MegaLL& ll, bool is_self, int s, int h, int r, int slot, int L, int P,
                                                   unsigned in_tag, unsigned out_tag, float* sc, float (*red)[64], float* stat, float* qs, float* kns,
-                                                  float* vns, int tid, AttnRegs<M2_WARPS>& R, int* err) {
+                                                  float* vns, int tid, AttnRegs<M2_WARPS>& R, int* err, unsigned long long* trace = nullptr) {
     constexpr int NW = M2_WARPS;
     constexpr int SC_ITERS = AttnRegs<NW>::SC_ITERS, PV_PRE = AttnRegs<NW>::PV_PRE;
     const int lane = tid & 31, warp = tid >> 5;
@@ -252,6 +170,7 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
         vns[lane * 2] = ll_val(w[2]); vns[lane * 2 + 1] = ll_val(w[3]);
     }
     __syncthreads();
+    if (trace && tid == 0) trace[2] = (unsigned long long)clock64();
     const float4 q0 = *reinterpret_cast<const float4*>(qs + sub * 8), q1 = *reinterpret_cast<const float4*>(qs + sub * 8 + 4);
 #pragma unroll
     for (int it = 0; it < SC_ITERS; ++it) {
@@ -268,6 +187,7 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
         if (kk < nk && sub == 0) sc[kk] = (R.kvalid[it] || is_new) ? dd : -INFINITY;
     }
     __syncthreads();
+    if (trace && tid == 0) trace[3] = (unsigned long long)clock64();
     if (warp < 4) {
         float pv[4];
         float m = -INFINITY;
@@ -323,6 +243,7 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
         red[warp][lane * 2 + 1] = o.y;
     }
     __syncthreads();
+    if (trace && tid == 0) trace[4] = (unsigned long long)clock64();
     if (tid < 64) {
         const float v = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
         if (p.n_splits == 1) {
@@ -352,32 +273,33 @@ __device__ __forceinline__ void m2_attention_merge(const DecAttnParams& p, const
             if (s < 32) { msh[s] = mv.x; msh[32 + s] = mv.y; }
         }
     }
-    float ov[8];
-    if (tid < 64 && S <= 8) {
-        ll_t oo[8];
+    constexpr int SB = 16;                             // splits merged with every load in flight at once (cross attention: 12 of them)
+    float ov[SB];
+    if (tid < 64 && S <= SB) {
+        ll_t oo[SB];
         long long spin = 0;
         while (true) {
             bool ok = true;
 #pragma unroll
-            for (int s = 0; s < 8; ++s)
+            for (int s = 0; s < SB; ++s)
                 if (s < S) asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(oo[s]) : "l"(base + (long long)s * M2_PART + tid) : "memory");
 #pragma unroll
-            for (int s = 0; s < 8; ++s)
+            for (int s = 0; s < SB; ++s)
                 if (s < S) ok = ok && (unsigned)(oo[s] >> 32) == tag;
             if (ok || !ll_spin_check(spin, err)) break;
         }
 #pragma unroll
-        for (int s = 0; s < 8; ++s) ov[s] = s < S ? ll_val(oo[s]) : 0.f;
+        for (int s = 0; s < SB; ++s) ov[s] = s < S ? ll_val(oo[s]) : 0.f;
     }
     __syncthreads();
     if (tid >= 64) return;
     float num = 0.f, den = 0.f;
     float mmax = -INFINITY;
-    if (S <= 8) {
+    if (S <= SB) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s) if (s < S) mmax = fmaxf(mmax, msh[s]);
+        for (int s = 0; s < SB; ++s) if (s < S) mmax = fmaxf(mmax, msh[s]);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
+        for (int s = 0; s < SB; ++s) {
             if (s < S && msh[32 + s] > 0.f) {
                 const float w = expf(msh[s] - mmax);
                 num = fmaf(w, ov[s], num);
@@ -412,6 +334,9 @@ __device__ __forceinline__ void m2_attention_merge(const DecAttnParams& p, const
 //   K4 = K / 4 float4 columns.  "grouped" (K4 a multiple of 32, <= 256: the d_model-wide inputs): G = 512 / K4 row groups, group rg
 //   takes rows rg, rg + G, ... and group 0 polls the activation for everybody (one CTA barrier).  Otherwise one group, thread t owns
 //   columns t and t + 512 (K4 <= 1024) and polls exactly what it multiplies.
+// CTA barrier over the first `count` threads only (named barrier 1): the LayerNorm statistics involve the warps that hold columns, not the
+// epilogue warps, which may still be storing the previous phase's rows
+__device__ __forceinline__ void m3_bar_cols(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 __device__ __forceinline__ float m3_dot4(const float4 w, const float4 x) {
     float t0 = w.x * x.x; t0 = fmaf(w.y, x.y, t0);
     float t1 = w.z * x.z; t1 = fmaf(w.w, x.w, t1);
@@ -419,26 +344,42 @@ __device__ __forceinline__ float m3_dot4(const float4 w, const float4 x) {
 }
 __device__ __forceinline__ float m3_tree8(const float* r) { return ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7])); }
 
-// 8 values per lane -> lane L (L % 4 == 0) holds the warp-wide sum of value index ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1)
-__device__ __forceinline__ float m3_reduce8(const float (&a)[8], int lane) {
-    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
-    float b[4], c[2];
+// P values per lane (P = 8, 16 or 32) -> one warp-wide sum per lane: the transposing butterfly halves the number of live values at every
+// level (lanes with the mask bit set keep the upper half and send the lower half), then plain xor-adds once a single value is left.
+// Every row is combined in the same order (xor 16, 8, 4, 2, 1) whatever P is, so a row's bits do not depend on how many rows ride along.
+// The lane's row index is m3_ridx<P>(lane); 32 / P lanes hold each row redundantly.
+template <int P>
+__device__ __forceinline__ float m3_reduce(float (&a)[P], int lane) {
+    int n = P;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = h16 ? a[i] : a[i + 4], keep = h16 ? a[i + 4] : a[i];
-        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
+    for (int m = 16; m >= 1; m >>= 1) {
+        if (n > 1) {
+            const bool hi = (lane & m) != 0;
+            const int h = n / 2;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = h8 ? b[i] : b[i + 2], keep = h8 ? b[i + 2] : b[i];
-        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            for (int i = 0; i < P / 2; ++i) {
+                if (i < h) {
+                    const float send = hi ? a[i] : a[i + h], keep = hi ? a[i + h] : a[i];
+                    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                }
+            }
+            n = h;
+        } else {
+            a[0] += __shfl_xor_sync(0xffffffffu, a[0], m);
+        }
     }
-    const float send = h4 ? c[0] : c[1], keep = h4 ? c[1] : c[0];
-    float v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v;
+    return a[0];
 }
+template <int P>
+__device__ __forceinline__ int m3_ridx(int lane) {
+    int r = 0, n = P;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1)
+        if (n > 1) { n /= 2; r += (lane & m) ? n : 0; }
+    return r;
+}
+template <int P>
+__device__ __forceinline__ bool m3_rowner(int lane) { return (lane & (32 / P - 1)) == 0; }      // one writer per row
 
 // Thread -> weight-column mapping of a K-wide input; K takes two values per model (d_model, ffn_dim): computed once per kernel.
 struct M3Map { int K4, G, rg, kq0, NS, npw, wi; bool grouped, in_group, active_warp; };
@@ -457,65 +398,329 @@ __device__ __forceinline__ M3Map m3_make_map(int K, int tid) {
     return m;
 }
 
-// One pass of <= 8 row slots: all weight loads first (branch-free: out-of-range rows re-read row 0 and are discarded by a select),
-// then the products, then the transposing butterfly.  Everything a phase does is a chain of dependent latencies, so no load may sit
-// behind a branch that waits for the previous row's arithmetic.
-template <int NB, int NS>
-__device__ __forceinline__ void m3_pass(const float* wb, int K, int R, int G, int rg, int p0, const int (&kqc)[2], const float4 (&xv)[NB][2],
+// All row slots of the phase in one go (P = 8, 16 or 32 slots): weights are loaded in chunks of 8 rows (8 x LDS.128 in flight, branch-free:
+// out-of-range rows re-read row 0 and are discarded by a select), every row slot keeps its own accumulator, and ONE butterfly reduces
+// all of them at the end.  A phase is a chain of dependent latencies: one shuffle chain per phase instead of one per 8 rows.
+template <int NB, int P>
+__device__ __forceinline__ void m3_rows(const float* wb, int K, int R, int G, int rg, int NS, const int (&kqc)[M3_NS], const float4 (&xv)[NB][M3_NS],
                                         float* red_b0, float* red_b1, int wi, int lane) {
-    float acc[NB][8];
-    float4 w[8][NS];
-    bool valid[8];
+    float acc[NB][P];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int lr = (p0 + i) * G + rg;
-        valid[i] = lr < R;
-        const float4* wrow = reinterpret_cast<const float4*>(wb + (valid[i] ? lr : 0) * K);
+    for (int c = 0; c < P / 8; ++c) {
+        const float4* wrow[8];
+        bool valid[8];
 #pragma unroll
-        for (int s = 0; s < NS; ++s) w[i][s] = wrow[kqc[s]];
-    }
+        for (int i = 0; i < 8; ++i) {
+            const int lr = (c * 8 + i) * G + rg;
+            valid[i] = lr < R;
+            wrow[i] = reinterpret_cast<const float4*>(wb + (valid[i] ? lr : 0) * K);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            float a = m3_dot4(w[i][0], xv[b][0]);
-            if (NS > 1) a += m3_dot4(w[i][NS - 1], xv[b][NS - 1]);
-            acc[b][i] = valid[i] ? a : 0.f;
+            for (int b = 0; b < NB; ++b) acc[b][c * 8 + i] = 0.f;
         }
+        if (c * 8 * G + rg < R) {             // (warp-uniform when G == 1; otherwise the selects below discard what the extra rows add)
+#pragma unroll
+            for (int s = 0; s < M3_NS; ++s) {
+                if (s < NS) {
+                    float4 w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = wrow[i][kqc[s]];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) acc[b][c * 8 + i] += m3_dot4(w[i], xv[b][s]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b][c * 8 + i] = valid[i] ? acc[b][c * 8 + i] : 0.f;
     }
-    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    const int lr = (p0 + ridx) * G + rg;
+    const int lr = m3_ridx<P>(lane) * G + rg;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        const float v = m3_reduce8(acc[b], lane);
-        if ((lane & 3) == 0 && lr < R) (b == 0 ? red_b0 : red_b1)[lr * M2_WARPS + wi] = v;
+        const float v = m3_reduce<P>(acc[b], lane);
+        if (m3_rowner<P>(lane) && lr < R) (b == 0 ? red_b0 : red_b1)[lr * M2_WARPS + wi] = v;
     }
 }
 
+// Per-thread poll geometry, computed once per kernel: where this thread's columns of the three GEMV inputs live (its replica of the
+// residual stream / merged heads / fc1 output) and which of its column slots exist.  A phase's first poll round is then two shared-memory
+// reads (which input, how many CTAs own rows) away from the phase top.
+struct M3Poll { const ll_t* x; const ll_t* att; const ll_t* h; unsigned mask_d, mask_f; };
+__device__ __forceinline__ M3Poll m3_make_poll(const MegaLL& ll, const M3Map& md, const M3Map& mf, int rep_off) {
+    M3Poll q;
+    q.x = ll.x + (long long)rep_off * ll.x_rep + md.kq0 * 4;
+    q.att = ll.att + (long long)rep_off * ll.x_rep + md.kq0 * 4;
+    q.h = ll.h + (long long)rep_off * ll.h_rep + mf.kq0 * 4;
+    q.mask_d = q.mask_f = 0;
+#pragma unroll
+    for (int s = 0; s < M3_NS; ++s) {
+        // grouped mapping: group 0 polls for everybody (one column each); else a thread polls exactly the columns it multiplies
+        if ((md.grouped ? md.rg == 0 && s == 0 : s < md.NS) && md.kq0 + s * M2_THREADS < md.K4) q.mask_d |= 1u << s;
+        if ((mf.grouped ? mf.rg == 0 && s == 0 : s < mf.NS) && mf.kq0 + s * M2_THREADS < mf.K4) q.mask_f |= 1u << s;
+    }
+    return q;
+}
+
+// ---- row-per-warp GEMV phase (inputs as wide as d_model: qkv, out, q_c, out_c, fc1, proj_out) ------------------------------------------
+// Measured on the K-split form (tools/mega3_trace.py): the multiply is instruction-issue bound, ~12 instructions per float4 product
+// (address, select, butterfly share) with only 6 of 8 warps busy.  For the d_model-wide inputs the activation is small enough to sit in
+// every warp's registers (K / 32 floats per lane), so each warp takes whole rows (warp, warp + 8, ...): one LDS.128 and four FFMA per
+// float4 product — gemv_dot's arithmetic and summation order, i.e. the same bits as the per-phase kernels and the barrier megakernel —
+// five shuffles per row, and the warp finishes its own rows (lane = row slot x replica: one store instruction writes every replica).
+// No cross-warp reduction, no epilogue hand-over: the phase's only CTA barrier is the one that publishes the activation.
 template <int NB, typename SM>
-__device__ __forceinline__ void m3_gemv_phase(const Mega2Params& mp, const Mega2Phase& ph2, SM& sm, const M3Map& mapd, const M3Map& mapf, int cta, int rep_off,
+__device__ __forceinline__ void m3_rw_tail(const Mega2Params& mp, const Mega2Phase& ph2, SM& sm, int cta, int tid, int buf, unsigned g_idx, int par,
+                                           unsigned in_tag, unsigned out_tag, int cur_pos, int* err, unsigned long long* trace,
+                                           ll_t (&w)[NB][M3_NS][4], const bool (&on)[NB][M3_NS], bool poller, const ll_t* in, int r0, int R) {
+    const MegaPhase& ph = ph2.base;
+    const GemvParams& g = ph.g;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int d = mp.d_model, K = d, K4 = d >> 2;
+    const bool ln = g.xmode == X_LAYERNORM;
+    // ---- epilogue operands of this lane: row slot ei = lane / 8 (rows warp, warp + 8, warp + 16, warp + 24), replica rep = lane % 8 ----
+    const int ei = lane >> 3, rep = lane & 7;
+    const int erow = warp + M2_WARPS * ei;
+    int act = 0;
+    float alpha = 1.f, bias_v = 0.f, res_v[NB];
+    ll_t* lo[NB];
+    float* plain[NB];
+    bool st0 = false, st1 = false;
+    long long rs8 = 0;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { res_v[b] = 0.f; lo[b] = nullptr; plain[b] = nullptr; }
+    if (erow < R) {
+        const int n = r0 + erow;
+        const int si = (int)(g.nseg > 1 && n >= g.seg[1].n_begin) + (int)(g.nseg > 2 && n >= g.seg[2].n_begin);
+        const GemvSeg& sg = g.seg[si];
+        const int col = n - sg.n_begin;
+        if (g.bias) bias_v = __ldg(g.bias + n);
+        act = sg.act; alpha = sg.alpha;
+        const long long rs = ph2.out_rs[si];
+        rs8 = 8 * rs;
+        const bool has_out = ph2.out_sel[si] != LL_NONE;
+        st0 = has_out && (rs ? rep < mp.ll.reps : rep == 0);
+        st1 = has_out && rs && rep + 8 < mp.ll.reps;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (b < mp.rows) {
+                if (ph2.res_xraw) res_v[b] = sm.xraw[b * d + n];
+                lo[b] = mp.ll.x + ph2.out_off[si] + (long long)b * ph2.out_bw[si] + col + rep * rs;
+                if (ph2.plain_out[si] && rep == 0) plain[b] = sg.out + (long long)b * sg.out_bs + (long long)cur_pos * sg.pos_stride + col;
+            }
+        }
+    }
+    const int kq0 = tid;                                   // pollers: thread t holds float4 column t (t < K4 <= 256)
+    float4 lw = make_float4(0, 0, 0, 0), lb = lw;
+    if (ln && poller) {
+        lw = __ldg(reinterpret_cast<const float4*>(g.ln_w) + kq0);
+        lb = __ldg(reinterpret_cast<const float4*>(g.ln_b) + kq0);
+    }
+    if (trace && tid == 0) trace[2] = (unsigned long long)clock64();
+    // ---- input ----
+    if (poller) {
+        long long spin = 0;
+        while (true) {
+            bool ok = true;
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                if (on[b][0]) ok = ok && ll_tag_ok4(w[b][0][0], w[b][0][1], w[b][0][2], w[b][0][3], in_tag);
+            if (ok || !ll_spin_check(spin, err)) break;
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                if (on[b][0]) {
+                    const ll_t* src = in + (long long)b * K + kq0 * 4;
+                    ll_load2(src, w[b][0][0], w[b][0][1]);
+                    ll_load2(src + 2, w[b][0][2], w[b][0][3]);
+                }
+        }
+        if (trace && tid == 0) { trace[4] = (unsigned long long)clock64(); trace[10] = (unsigned long long)spin; }
+    }
+    float* xs = sm.xrw[par];
+    if (R > 0) {
+        float4 raw[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+            raw[b] = on[b][0] ? make_float4(ll_val(w[b][0][0]), ll_val(w[b][0][1]), ll_val(w[b][0][2]), ll_val(w[b][0][3])) : make_float4(0, 0, 0, 0);
+        const int npl = (K4 + 31) >> 5;
+        if (ln) {
+            // LayerNorm with the reduction structure of gemv_stage_x (32-float4 chunks per warp, 8 chunk partials, fixed tree)
+            if (warp < npl) {
+                const float inv = 1.0f / (float)K;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const float sc = warp_sum((raw[b].x + raw[b].y) + (raw[b].z + raw[b].w));
+                    if (lane == 0) sm.ln_red[b * 8 + warp] = sc;
+                    if (poller) reinterpret_cast<float4*>(sm.xraw + b * K)[kq0] = raw[b];
+                }
+                m3_bar_cols(npl * 32);
+                if (trace && tid == 0) trace[5] = (unsigned long long)clock64();
+                float mean[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    mean[b] = m3_tree8(sm.ln_red + b * 8) * inv;
+                    float q = 0.f;
+                    if (poller && b < mp.rows) {
+                        const float a0 = raw[b].x - mean[b], a1 = raw[b].y - mean[b], a2 = raw[b].z - mean[b], a3 = raw[b].w - mean[b];
+                        q = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                    }
+                    q = warp_sum(q);
+                    if (lane == 0) sm.ln_red2[b * 8 + warp] = q;
+                }
+                m3_bar_cols(npl * 32);
+                if (poller) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        float4 o = make_float4(0, 0, 0, 0);
+                        if (b < mp.rows) {
+                            const float rstd = rsqrtf(m3_tree8(sm.ln_red2 + b * 8) * inv + g.eps);
+                            o.x = (raw[b].x - mean[b]) * rstd * lw.x + lb.x; o.y = (raw[b].y - mean[b]) * rstd * lw.y + lb.y;
+                            o.z = (raw[b].z - mean[b]) * rstd * lw.z + lb.z; o.w = (raw[b].w - mean[b]) * rstd * lw.w + lb.w;
+                        }
+                        reinterpret_cast<float4*>(xs + b * K)[kq0] = o;
+                    }
+                }
+            }
+        } else if (poller) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) reinterpret_cast<float4*>(xs + b * K)[kq0] = raw[b];
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");   // next phase's descriptor (issued at the top of the phase loop)
+    __syncthreads();                                   // activation published; next descriptor landed
+    if (trace && tid == 0) trace[6] = (unsigned long long)clock64();
+    wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err);
+    if (trace && tid == 0) trace[3] = (unsigned long long)clock64();
+
+    float sum[NB][4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sum[b][i] = 0.f;
+    if (R > 0 && warp < R && !(c_ll_debug & 4)) {
+        constexpr int XS = 8;                              // float4 of the activation per lane (d_model <= 1024)
+        const int nx = (K4 + 31) >> 5;
+        float4 xr[NB][XS];
+        const float4* xs4 = reinterpret_cast<const float4*>(xs);
+#pragma unroll
+        for (int j = 0; j < XS; ++j) {
+            const int col = j * 32 + lane;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) xr[b][j] = (j < nx && col < K4 && b < mp.rows) ? xs4[b * K4 + col] : make_float4(0, 0, 0, 0);
+        }
+        const float4* wb4 = reinterpret_cast<const float4*>(sm.wbuf[buf]);
+        float4 acc[NB][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b][i] = make_float4(0, 0, 0, 0);
+            const int row = warp + M2_WARPS * i;
+            if (row < R) {                                 // warp-uniform
+                const float4* wrow = wb4 + row * K4;
+#pragma unroll
+                for (int j = 0; j < XS; ++j) {
+                    if (j < nx) {
+                        const int col = j * 32 + lane;
+                        const float4 wv = wrow[col < K4 ? col : 0];      // (x is zero beyond K4)
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+                            acc[b][i].x = fmaf(wv.x, xr[b][j].x, acc[b][i].x); acc[b][i].y = fmaf(wv.y, xr[b][j].y, acc[b][i].y);
+                            acc[b][i].z = fmaf(wv.z, xr[b][j].z, acc[b][i].z); acc[b][i].w = fmaf(wv.w, xr[b][j].w, acc[b][i].w);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) sum[b][i] = warp_sum((acc[b][i].x + acc[b][i].y) + (acc[b][i].z + acc[b][i].w));
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.wfree[buf]);            // this warp no longer reads the weight slice
+    if (trace && tid == 0) trace[7] = (unsigned long long)clock64();
+    // ---- epilogue in the warp that owns the rows ----
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        if (lo[b]) {
+            float v = ei == 0 ? sum[b][0] : (ei == 1 ? sum[b][1] : (ei == 2 ? sum[b][2] : sum[b][3]));
+            v += bias_v;
+            v = apply_act(v, act) * alpha;
+            v += res_v[b];
+            if (st0) ll_store(lo[b], v, out_tag);
+            if (st1) ll_store(lo[b] + rs8, v, out_tag);
+            if (plain[b]) {
+                *plain[b] = v;
+                __threadfence();                           // K/V cache rows are read by LATER tokens through plain loads (see the header comment)
+            }
+        }
+    }
+    if (trace && tid == 0) { trace[8] = (unsigned long long)clock64(); trace[9] = trace[8]; }
+}
+
+template <int NB, typename SM>
+__device__ __forceinline__ void m3_gemv_phase(const Mega2Params& mp, const Mega2Phase& ph2, SM& sm, const M3Map& mapd, const M3Map& mapf, const M3Poll& pl, int cta,
                                               int tid, unsigned g_idx, int par, unsigned in_tag, unsigned out_tag, int cur_pos, int* err,
-                                              unsigned long long* trace /* null or [8] */) {
+                                              unsigned long long* trace /* null or [16] */) {
+    // ---- the first poll round goes out before anything else: which input, does this CTA own rows — then the loads ----
+    const int isel = ph2.in_sel;
+    const bool has_rows = cta < ph2.n_active;
+    const bool in_h = isel == LL_H;
+    const ll_t* const pin = in_h ? pl.h : (isel == LL_ATT ? pl.att : pl.x);
+    const unsigned pmask = has_rows ? (in_h ? pl.mask_f : pl.mask_d) : 0u;
+    const int Kin = in_h ? mp.ffn_dim : mp.d_model;
+    ll_t w[NB][M3_NS][4];
+    bool on[NB][M3_NS];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int s = 0; s < M3_NS; ++s) {
+            on[b][s] = ((pmask >> s) & 1u) != 0 && b < mp.rows;
+            w[b][s][0] = w[b][s][1] = w[b][s][2] = w[b][s][3] = 0;
+            if (on[b][s]) {
+                const ll_t* src = pin + (long long)b * Kin + s * (M2_THREADS * 4);
+                ll_load2(src, w[b][s][0], w[b][s][1]);
+                ll_load2(src + 2, w[b][s][2], w[b][s][3]);
+            }
+        }
+    const bool poller = pmask != 0;
     const MegaPhase& ph = ph2.base;
     const GemvParams& g = ph.g;
     const int lane = tid & 31, warp = tid >> 5;
     const int buf = g_idx & 1;
     const int d = mp.d_model;
     const int K = g.K;
-    const bool isd = K == d;
+    const bool isd = !in_h;
     const int K4 = K >> 2;
     const bool grouped = isd ? mapd.grouped : mapf.grouped, in_group = isd ? mapd.in_group : mapf.in_group, active_warp = isd ? mapd.active_warp : mapf.active_warp;
     const int G = isd ? mapd.G : mapf.G, rg = isd ? mapd.rg : mapf.rg, kq0 = isd ? mapd.kq0 : mapf.kq0, NS = isd ? mapd.NS : mapf.NS,
               npw = isd ? mapd.npw : mapf.npw, wi = isd ? mapd.wi : mapf.wi;
-    // Every thread is past the barrier of the previous GEMV phase, i.e. nobody reads the other weight buffer any more: request the next
-    // GEMV's slice right away (a whole phase of lead).  Thread 416 has no columns in the grouped d_model mapping (K4 = 192).
-    if (tid == M2_THREADS - 96) prefetch_weights(ph.nx_W, ph.nx_ldw, ph.nx_N, ph.nx_K, sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, ph.nx_rpc);
     int r0, r1;
     cta_rows(g.N, cta, ph.rpc, r0, r1);
     const int R = r1 - r0;
     const bool ln = g.xmode == X_LAYERNORM;
+    const bool shared = ln || grouped;
+    const ll_t* in = pin - kq0 * 4;
+    if (trace && tid == 0) trace[1] = (unsigned long long)clock64();
+    // The next GEMV's weight slice goes into the buffer the PREVIOUS GEMV phase read: requested as soon as every warp has signalled that
+    // it is done with it (a whole phase of lead for the copy).
+    if (tid == M2_THREADS - 32) {
+        if (g_idx > 0) wait_weights(&sm.wfree[buf ^ 1], ((g_idx - 1) >> 1) & 1, err);      // every warp has finished reading the slice of GEMV phase g_idx - 1
+        prefetch_weights(ph.nx_W, ph.nx_ldw, ph.nx_N, ph.nx_K, sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, ph.nx_rpc);
+    }
+    if (isd) {
+        m3_rw_tail<NB>(mp, ph2, sm, cta, tid, buf, g_idx, par, in_tag, out_tag, cur_pos, err, trace, w, on, poller, in, r0, R);
+        return;
+    }
+    const bool has_col = in_group && kq0 < K4;
+    float4 lw = make_float4(0, 0, 0, 0), lb = lw;
+    if (ln && has_col) {
+        lw = __ldg(reinterpret_cast<const float4*>(g.ln_w) + kq0);
+        lb = __ldg(reinterpret_cast<const float4*>(g.ln_b) + kq0);
+    }
 
-    // ---- epilogue operands, fetched NOW by the threads that will finish the rows (warps 14 / 15: thread 448 + e finishes decoder row e / R,
+    // ---- epilogue operands, fetched NOW by the threads that will finish the rows (warps 6 / 7: thread 192 + e finishes decoder row e / R,
     //      output row e % R), so that nothing but the sum itself is left behind the barrier ----
     const int e = tid - (M2_THREADS - 64);
     bool epi = false;
@@ -532,70 +737,62 @@ __device__ __forceinline__ void m3_gemv_phase(const Mega2Params& mp, const Mega2
             const int n = r0 + elr;
             const int si = (int)(g.nseg > 1 && n >= g.seg[1].n_begin) + (int)(g.nseg > 2 && n >= g.seg[2].n_begin);
             const GemvSeg& sg = g.seg[si];
-            const int osel = ph2.out_sel[si], col = n - sg.n_begin;
+            const int col = n - sg.n_begin;
             if (g.bias) bias_v = __ldg(g.bias + n);
             if (ph2.res_xraw) res_v = sm.xraw[eb * d + n];
             act = sg.act; alpha = sg.alpha;
-            if (osel == LL_X || osel == LL_H) {
-                const long long width = osel == LL_H ? g.N : d;
-                ll_rs = osel == LL_H ? mp.ll.h_rep : mp.ll.x_rep;
-                ll_out = (osel == LL_H ? mp.ll.h : mp.ll.x) + (long long)eb * width + col;
-                ll_nrep = mp.ll.reps;
-            } else if (osel != LL_NONE) {
-                const long long width = osel == LL_K || osel == LL_V ? 2 * d : (osel == LL_LOGITS ? mp.V : d);
-                ll_out = ll_buf(mp.ll, osel) + (long long)eb * width + (osel == LL_V ? d : 0) + col;
-                ll_nrep = 1;
+            if (ph2.out_sel[si] != LL_NONE) {
+                ll_out = mp.ll.x + ph2.out_off[si] + (long long)eb * ph2.out_bw[si] + col;
+                ll_rs = ph2.out_rs[si];
+                ll_nrep = ph2.out_rs[si] ? mp.ll.reps : 1;
             }
             if (ph2.plain_out[si]) plain = sg.out + (long long)eb * sg.out_bs + (long long)cur_pos * sg.pos_stride + col;
         }
     }
 
+    if (trace && tid == 0) trace[2] = (unsigned long long)clock64();
+    if (active_warp) wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err);        // requested a phase ago (only the warps that multiply need it)
+    if (trace && tid == 0) trace[3] = (unsigned long long)clock64();
+
     // ---- input: polled straight into registers ----
-    float4 xv[NB][2];
+    float4 xv[NB][M3_NS];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { xv[b][0] = make_float4(0, 0, 0, 0); xv[b][1] = make_float4(0, 0, 0, 0); }
-    bool weights_waited = false;
-    if (R > 0) {
-        const ll_t* in = (ph2.in_sel == LL_H ? mp.ll.h + (long long)rep_off * mp.ll.h_rep
-                                             : (ph2.in_sel == LL_ATT ? mp.ll.att : mp.ll.x) + (long long)rep_off * mp.ll.x_rep);
-        if (ln || grouped) {
-            // one group polls (tid < K4), everybody else picks the values up from shared memory after the barrier
-            const bool poller = rg == 0 && kq0 < K4;
-            const bool has_col = in_group && kq0 < K4;
-            float4 lw = make_float4(0, 0, 0, 0), lb = lw;
-            if (ln && has_col) {
-                lw = __ldg(reinterpret_cast<const float4*>(g.ln_w) + kq0);
-                lb = __ldg(reinterpret_cast<const float4*>(g.ln_b) + kq0);
-            }
-            float4 raw[NB];
-            {
-                ll_t w[NB][4];
+    for (int b = 0; b < NB; ++b)
 #pragma unroll
-                for (int b = 0; b < NB; ++b) { w[b][0] = w[b][1] = w[b][2] = w[b][3] = 0; }
-                if (poller) {
-                    long long spin = 0;
-                    bool first = true;
-                    while (true) {
+        for (int s = 0; s < M3_NS; ++s) xv[b][s] = make_float4(0, 0, 0, 0);
+    if (poller) {
+        long long spin = 0;
+        while (true) {
+            bool ok = true;
 #pragma unroll
-                        for (int b = 0; b < NB; ++b)
-                            if (b < g.B) { const ll_t* src = in + (long long)b * K + kq0 * 4; ll_load2(src, w[b][0], w[b][1]); ll_load2(src + 2, w[b][2], w[b][3]); }
-                        if (first) { wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err); first = false; }      // overlaps the first round trip
-                        bool ok = true;
+            for (int b = 0; b < NB; ++b)
 #pragma unroll
-                        for (int b = 0; b < NB; ++b)
-                            if (b < g.B) ok = ok && ll_tag_ok4(w[b][0], w[b][1], w[b][2], w[b][3], in_tag);
-                        if (ok || !ll_spin_check(spin, err)) break;
+                for (int s = 0; s < M3_NS; ++s)
+                    if (on[b][s]) ok = ok && ll_tag_ok4(w[b][s][0], w[b][s][1], w[b][s][2], w[b][s][3], in_tag);
+            if (ok || !ll_spin_check(spin, err)) break;
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int s = 0; s < M3_NS; ++s)
+                    if (on[b][s]) {
+                        const ll_t* src = in + (long long)b * K + (kq0 + s * M2_THREADS) * 4;
+                        ll_load2(src, w[b][s][0], w[b][s][1]);
+                        ll_load2(src + 2, w[b][s][2], w[b][s][3]);
                     }
-                    weights_waited = true;
-                    if (trace && tid == 0) { trace[1] = (unsigned long long)clock64(); trace[7] = (unsigned long long)spin; }
-                }
+        }
+        if (trace && tid == 0) { trace[4] = (unsigned long long)clock64(); trace[10] = (unsigned long long)spin; }
+    }
+    const int ncols = grouped ? G * K4 : npw * 32;      // threads of the warps that hold columns (whole warps, from thread 0)
+    if (R > 0 && active_warp) {
+        if (shared) {
+            float4 raw[NB];
 #pragma unroll
-                for (int b = 0; b < NB; ++b)
-                    raw[b] = (poller && b < g.B) ? make_float4(ll_val(w[b][0]), ll_val(w[b][1]), ll_val(w[b][2]), ll_val(w[b][3])) : make_float4(0, 0, 0, 0);
-            }
+            for (int b = 0; b < NB; ++b)
+                raw[b] = on[b][0] ? make_float4(ll_val(w[b][0][0]), ll_val(w[b][0][1]), ll_val(w[b][0][2]), ll_val(w[b][0][3])) : make_float4(0, 0, 0, 0);
+            const bool pol = poller;
             if (ln) {
-                // LayerNorm with the reduction structure of gemv_stage_x / m2_stage_ln (32-float4 chunks per warp, 8 chunk partials, fixed tree):
-                // the normalised activations carry the same bits as in the other token-loop drivers.
+                // LayerNorm with the reduction structure of gemv_stage_x (32-float4 chunks per warp, 8 chunk partials, fixed tree): the
+                // normalised activations carry the same bits as in the other token-loop drivers.
                 const int npl = (K4 + 31) >> 5;
                 const float inv = 1.0f / (float)K;
                 if (warp < npl) {
@@ -603,10 +800,11 @@ __device__ __forceinline__ void m3_gemv_phase(const Mega2Params& mp, const Mega2
                     for (int b = 0; b < NB; ++b) {
                         const float sc = warp_sum((raw[b].x + raw[b].y) + (raw[b].z + raw[b].w));
                         if (lane == 0) sm.ln_red[b * 8 + warp] = sc;
-                        if (poller) reinterpret_cast<float4*>(sm.xraw + b * K)[kq0] = raw[b];
+                        if (pol) reinterpret_cast<float4*>(sm.xraw + b * K)[kq0] = raw[b];
                     }
                 }
-                __syncthreads();
+                m3_bar_cols(ncols);
+                if (trace && tid == 0) trace[5] = (unsigned long long)clock64();
                 float mean[NB];
 #pragma unroll
                 for (int b = 0; b < NB; ++b) mean[b] = m3_tree8(sm.ln_red + b * 8) * inv;
@@ -614,7 +812,7 @@ __device__ __forceinline__ void m3_gemv_phase(const Mega2Params& mp, const Mega2
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
                         float q = 0.f;
-                        if (poller && b < g.B) {
+                        if (pol && b < g.B) {
                             const float a0 = raw[b].x - mean[b], a1 = raw[b].y - mean[b], a2 = raw[b].z - mean[b], a3 = raw[b].w - mean[b];
                             q = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
                         }
@@ -622,122 +820,89 @@ __device__ __forceinline__ void m3_gemv_phase(const Mega2Params& mp, const Mega2
                         if (lane == 0) sm.ln_red2[b * 8 + warp] = q;
                     }
                 }
-                __syncthreads();
+                m3_bar_cols(ncols);
                 if (has_col) {
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
                         if (b < g.B) {
                             const float rstd = rsqrtf(m3_tree8(sm.ln_red2 + b * 8) * inv + g.eps);
-                            const float4 v = poller ? raw[b] : reinterpret_cast<const float4*>(sm.xraw + b * K)[kq0];
+                            const float4 v = pol ? raw[b] : reinterpret_cast<const float4*>(sm.xraw + b * K)[kq0];
                             xv[b][0].x = (v.x - mean[b]) * rstd * lw.x + lb.x; xv[b][0].y = (v.y - mean[b]) * rstd * lw.y + lb.y;
                             xv[b][0].z = (v.z - mean[b]) * rstd * lw.z + lb.z; xv[b][0].w = (v.w - mean[b]) * rstd * lw.w + lb.w;
                         }
                     }
                 }
             } else {
-                if (poller) {
+                if (G > 1) {            // more than one row group: hand the polled columns over through shared memory
+                    if (pol) {
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) reinterpret_cast<float4*>(sm.u.xs + b * K)[kq0] = raw[b];
+                        for (int b = 0; b < NB; ++b) reinterpret_cast<float4*>(sm.u.xs + b * K)[kq0] = raw[b];
+                    }
+                    m3_bar_cols(ncols);
                 }
-                __syncthreads();
                 if (has_col) {
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) xv[b][0] = poller ? raw[b] : reinterpret_cast<const float4*>(sm.u.xs + b * K)[kq0];
+                    for (int b = 0; b < NB; ++b) xv[b][0] = pol ? raw[b] : reinterpret_cast<const float4*>(sm.u.xs + b * K)[kq0];
                 }
             }
         } else {
-            // one group: every thread polls exactly the columns it multiplies, all loads in flight before the first tag check
-            ll_t w[NB][2][4];
-            bool on[NB][2];
 #pragma unroll
             for (int b = 0; b < NB; ++b)
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    on[b][s] = b < g.B && s < NS && kq0 + s * M2_THREADS < K4;
-                    w[b][s][0] = w[b][s][1] = w[b][s][2] = w[b][s][3] = 0;
-                }
-            long long spin = 0;
-            bool first = true;
-            while (true) {
-#pragma unroll
-                for (int b = 0; b < NB; ++b)
-#pragma unroll
-                    for (int s = 0; s < 2; ++s)
-                        if (on[b][s]) {
-                            const ll_t* src = in + (long long)b * K + (kq0 + s * M2_THREADS) * 4;
-                            ll_load2(src, w[b][s][0], w[b][s][1]);
-                            ll_load2(src + 2, w[b][s][2], w[b][s][3]);
-                        }
-                if (first) { wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err); first = false; }
-                bool ok = true;
-#pragma unroll
-                for (int b = 0; b < NB; ++b)
-#pragma unroll
-                    for (int s = 0; s < 2; ++s)
-                        if (on[b][s]) ok = ok && ll_tag_ok4(w[b][s][0], w[b][s][1], w[b][s][2], w[b][s][3], in_tag);
-                if (ok || !ll_spin_check(spin, err)) break;
-            }
-            weights_waited = true;
-            if (trace && tid == 0) { trace[1] = (unsigned long long)clock64(); trace[7] = (unsigned long long)spin; }
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int s = 0; s < 2; ++s)
+                for (int s = 0; s < M3_NS; ++s)
                     if (on[b][s]) xv[b][s] = make_float4(ll_val(w[b][s][0]), ll_val(w[b][s][1]), ll_val(w[b][s][2]), ll_val(w[b][s][3]));
         }
     }
-    if (trace && tid == 0) trace[2] = (unsigned long long)clock64();
-    if (!weights_waited) wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err);      // every thread observes the phase of the mbarrier it will wait on next time
-    if (trace && tid == 0) trace[3] = (unsigned long long)clock64();
+    if (trace && tid == 0) trace[6] = (unsigned long long)clock64();
 
     // ---- multiply + reduce ----
     if (R > 0 && active_warp && !(c_ll_debug & 4)) {
         const int Pn = G == 1 ? R : (G == 2 ? (R + 1) >> 1 : (R + G - 1) / G);       // row slots per thread (host guarantees <= M3_SLOTS)
         const float* wb = sm.wbuf[buf];
-        int kqc[2];
-        kqc[0] = kq0 < K4 ? kq0 : 0;
-        kqc[1] = kq0 + M2_THREADS < K4 ? kq0 + M2_THREADS : 0;
+        int kqc[M3_NS];
+#pragma unroll
+        for (int s = 0; s < M3_NS; ++s) kqc[s] = kq0 + s * M2_THREADS < K4 ? kq0 + s * M2_THREADS : 0;
         float* red0 = &sm.red[par][0][0][0];
         float* red1 = &sm.red[par][NB - 1][0][0];
-#pragma unroll 1
-        for (int p0 = 0; p0 < Pn; p0 += 8) {
-            if (NS == 1) m3_pass<NB, 1>(wb, K, R, G, rg, p0, kqc, xv, red0, red1, wi, lane);
-            else         m3_pass<NB, 2>(wb, K, R, G, rg, p0, kqc, xv, red0, red1, wi, lane);
-        }
+        if (Pn <= 8)       m3_rows<NB, 8>(wb, K, R, G, rg, NS, kqc, xv, red0, red1, wi, lane);
+        else if (Pn <= 16) m3_rows<NB, 16>(wb, K, R, G, rg, NS, kqc, xv, red0, red1, wi, lane);
+        else               m3_rows<NB, 32>(wb, K, R, G, rg, NS, kqc, xv, red0, red1, wi, lane);
     }
-    if (trace && tid == 0) trace[4] = (unsigned long long)clock64();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.wfree[buf]);        // this warp no longer reads the weight slice
+    if (trace && tid == 0) trace[7] = (unsigned long long)clock64();
     asm volatile("cp.async.wait_all;" ::: "memory");   // next phase's descriptor (issued at the top of the phase loop)
     __syncthreads();
-    if (trace && tid == 0) trace[5] = (unsigned long long)clock64();
+    if (trace && tid == 0) trace[8] = (unsigned long long)clock64();
 
-    // ---- epilogue: sum of the warp partials (fixed tree over 16 slots, unused ones read as zero), bias / activation / residual, tagged store ----
+    // ---- epilogue: sum of the warp partials (fixed tree over 8 slots, unused ones read as zero), bias / activation / residual, tagged store ----
     if (epi) {
         const float4* r4 = reinterpret_cast<const float4*>(&sm.red[par][eb][elr][0]);
-        float4 q[4];
+        const float4 q0 = r4[0], q1 = r4[1];
+        float t[M2_WARPS] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) q[i] = r4[i];
-        float t[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w, q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) t[i] = i < npw ? t[i] : 0.f;
-        float v = (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) + (((t[8] + t[9]) + (t[10] + t[11])) + ((t[12] + t[13]) + (t[14] + t[15])));
+        for (int i = 0; i < M2_WARPS; ++i) t[i] = i < npw ? t[i] : 0.f;
+        float v = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
         v += bias_v;
         v = apply_act(v, act) * alpha;
         v += res_v;
-        for (int rep = 0; rep < ll_nrep; ++rep) ll_store(ll_out + rep * ll_rs, v, out_tag);
+        if (ll_nrep == 1) ll_store(ll_out, v, out_tag);
+        else {
+#pragma unroll
+            for (int rep = 0; rep < MEGA_LL_MAX_REPS; ++rep)
+                if (rep < ll_nrep) ll_store(ll_out + rep * ll_rs, v, out_tag);
+        }
         if (plain) {
             *plain = v;
             __threadfence();                           // K/V cache rows are read by LATER tokens through plain loads (see the header comment)
         }
-        if (trace && e == 0) trace[6] = (unsigned long long)clock64();
+        if (trace && e == 0) trace[9] = (unsigned long long)clock64();
     }
 }
 
 // TRACE = true is a separate instantiation for tools/mega2_trace.py: CTAs 0, 1, 100 and 140 stamp clock64 at four points of every phase
 // of token `trace_step` (phase start, input staged, weights landed, rows / units done); the production kernel carries no stamp code.
-// MODE 0: GEMV phases stage the activation in shared memory and give every warp whole output rows (the barrier kernel's gemv_dot).
-// MODE 1: K-split GEMV phases (m3_*): every thread polls ITS k-slice of the activation straight into registers, multiplies it with
-//         its slice of every weight row the CTA owns, and the CTA reduces the partial sums (warp butterfly + 16 warp partials).
-template <int NB, bool TRACE, int MODE>
+template <int NB, bool TRACE>
 __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Params mp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     M2Smem& sm = *reinterpret_cast<M2Smem*>(smem_raw);
@@ -750,10 +915,13 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
         sm.sample_params = mp.sample;
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
+        mbar_init(&sm.wfree[0], M2_WARPS);
+        mbar_init(&sm.wfree[1], M2_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     m2_clear_ln_red(sm.ln_red, tid);
     m2_clear_ln_red(sm.ln_red2, tid);
+    if (c_ll_debug & 1) for (int i = tid; i < 2 * MEGA_WBUF_FLOATS; i += M2_THREADS) (&sm.wbuf[0][0])[i] = 0.f;      // diagnostics: no weight stream, finite numbers
     __syncthreads();
     unsigned int g_idx = 0;          // running index of GEMV phases (selects weight buffer + mbarrier parity)
     if (tid == 0) {
@@ -780,7 +948,7 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
     int cur = 0;
     AttnRegs<M2_WARPS> areg;
     const M3Map mapd = m3_make_map(mp.d_model, tid), mapf = m3_make_map(mp.ffn_dim > 0 ? mp.ffn_dim : mp.d_model, tid);
-    const int rep_off = cta % mp.ll.reps;
+    const M3Poll pl = m3_make_poll(mp.ll, mapd, mapf, cta % mp.ll.reps);
 
     for (int step = 0; step < mp.max_steps; ++step) {
         if (tid == 0) {      // token header: written by the selection phase of the previous token (or the prologue above)
@@ -794,10 +962,9 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
         __syncthreads();
         const int cur_pos = sm.ctrl[0] - 1, fin = sm.ctrl[1], e = sm.ctrl[2], P = sm.ctrl[3];
         if (fin || e) break;
-        const int tslot = cta == 0 ? 0 : (cta == 1 ? 1 : (cta == 100 ? 2 : (cta == 140 ? 3 : -1)));
+        const int tslot = cta == mp.trace_cta ? 0 : -1;
         const bool tracing = TRACE && mp.trace != nullptr && step == mp.trace_step && tslot >= 0 && tid == 0;
-#define M2_TRACE(slot) do { if (tracing) { if (MODE == 1) { if (tslot < 2) mp.trace[((long long)tslot * mp.n_phases + pi) * 8 + ((slot) == 3 ? 5 : (slot))] = (unsigned long long)clock64(); } \
-                                           else mp.trace[((long long)tslot * mp.n_phases + pi) * 4 + (slot)] = (unsigned long long)clock64(); } } while (0)
+#define M2_TRACE(slot) do { if (tracing) mp.trace[(long long)pi * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
         for (int pi = 0; pi < mp.n_phases; ++pi) {
             M2_TRACE(0);
             const Mega2Phase& ph2 = sm.phase[cur];
@@ -807,81 +974,16 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
             // next phase's descriptor: global -> shared asynchronously, drained before the end-of-phase CTA barrier
             constexpr int DESC_WORDS = (int)(sizeof(Mega2Phase) / 4);
             const int nxt = cur == 2 ? 0 : cur + 1;
-            // (K-split mode: by warps 12..15, which hold no columns of the d_model-wide inputs, so the pollers start polling at once)
-            for (int i = MODE == 1 ? tid - 384 : tid; i >= 0 && i < DESC_WORDS; i += MODE == 1 ? 128 : M2_THREADS) {
+            // (by warps 6 / 7, which hold no columns of the d_model-wide inputs, so the pollers start polling at once)
+            for (int i = tid - (M2_THREADS - 64); i >= 0 && i < DESC_WORDS; i += 64) {
                 const int* src = reinterpret_cast<const int*>(&mp.phases[pi + 1 < mp.n_phases ? pi + 1 : 0]) + i;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(reinterpret_cast<int*>(&sm.phase[nxt]) + i)), "l"(src) : "memory");
             }
-            if (ph.kind == 0 && MODE == 1) {
-                // finer timeline than MODE 0: CTAs 0 and 1 only, 8 stamps per phase (0 start, 1 polled, 2 input ready, 3 weights landed,
-                // 4 partial sums written, 5 past the barrier, 6 epilogue of output row 0 stored, 7 = failed polls of thread 0)
+            if (ph.kind == 0) {
+                // timeline (TRACE instantiation, CTA mp.trace_cta): 16 stamps per phase, see tools/mega3_trace.py
                 unsigned long long* tr = nullptr;
-                if (TRACE && mp.trace != nullptr && step == mp.trace_step && cta < 2) {
-                    tr = mp.trace + ((long long)cta * mp.n_phases + pi) * 8;
-                    if (tid == 0) tr[0] = (unsigned long long)clock64();
-                }
-                m3_gemv_phase<NB>(mp, ph2, sm, mapd, mapf, cta, rep_off, tid, g_idx, pi & 1, in_tag, out_tag, cur_pos, err, tr);
-                ++g_idx;
-            } else if (ph.kind == 0) {
-                const GemvParams& g = ph.g;
-                const int buf = g_idx & 1;
-                int r0, r1;
-                cta_rows(g.N, cta, ph.rpc, r0, r1);
-                // bias of this warp's rows: lane j*NB + b holds it for the warp's j-th row (fetched while the input is still on its way)
-                float bias_pref = 0.f;
-                {
-                    const int n = r0 + warp + (lane / NB) * M2_WARPS;
-                    if (n < r1 && g.bias) bias_pref = __ldg(g.bias + n);
-                }
-                if (r0 < r1) {
-                    const ll_t* in = ll_buf(mp.ll, ph2.in_sel) + (cta % mp.ll.reps) * (ph2.in_sel == LL_H ? mp.ll.h_rep : mp.ll.x_rep);
-                    if (g.xmode == X_LAYERNORM) m2_stage_ln<NB>(g, in, in_tag, sm.u.xs, sm.xraw, sm.ln_red, tid, err);
-                    else m2_stage_plain<NB>(g, in, in_tag, sm.u.xs, tid, err);
-                }
-                __syncthreads();
-                M2_TRACE(1);
-                // the next GEMV's weight slice is requested only now (after this phase's small latency-critical loads), by the last warp
-                if (tid == M2_THREADS - 32) prefetch_weights(ph.nx_W, ph.nx_ldw, ph.nx_N, ph.nx_K, sm.wbuf[buf ^ 1], &sm.mbar[buf ^ 1], cta, ph.nx_rpc);
-                wait_weights(&sm.mbar[buf], (g_idx >> 1) & 1, err);
-                M2_TRACE(2);
-                int j = 0;
-#pragma unroll 1
-                for (int n = r0 + warp; n < r1; n += M2_WARPS, ++j) {
-                    const float bias_v = __shfl_sync(0xffffffffu, bias_pref, (j * NB) & 31);
-                    const int si = (int)(g.nseg > 1 && n >= g.seg[1].n_begin) + (int)(g.nseg > 2 && n >= g.seg[2].n_begin);
-                    const GemvSeg& sg = g.seg[si];
-                    const int osel = ph2.out_sel[si];
-                    const float mine = gemv_dot<NB, false>(g.K, sm.wbuf[buf] + (long long)(n - r0) * g.K, sm.u.xs, lane);
-                    float v = 0.f;
-                    if (lane < NB && lane < g.B) {
-                        v = mine;
-                        if (g.bias) v += bias_v;
-                        v = apply_act(v, sg.act) * sg.alpha;
-                        if (ph2.res_xraw) v += sm.xraw[lane * d + n];
-                    }
-                    if (osel == LL_X || osel == LL_H) {
-                        // replicated buffers: lane l stores replica l / NB of decoder row l % NB (the value comes from lane l % NB)
-                        const int b = lane % NB, rep = lane / NB;
-                        const float vb = __shfl_sync(0xffffffffu, v, b);
-                        if (rep < mp.ll.reps && b < g.B) {
-                            const long long width = osel == LL_H ? g.N : d;
-                            ll_store(ll_buf(mp.ll, osel) + rep * (osel == LL_H ? mp.ll.h_rep : mp.ll.x_rep) + (long long)b * width + (n - sg.n_begin), vb, out_tag);
-                        }
-                    } else if (lane < NB && lane < g.B) {
-                        if (osel != LL_NONE) {         // the tagged copy first: it is what this token's next phase waits for
-                            ll_t* out = ll_buf(mp.ll, osel);
-                            const long long width = osel == LL_K || osel == LL_V ? 2 * d : (osel == LL_LOGITS ? mp.V : d);
-                            const int col = osel == LL_V ? d + (n - sg.n_begin) : (n - sg.n_begin);
-                            ll_store(out + (long long)lane * width + col, v, out_tag);
-                        }
-                        if (ph2.plain_out[si]) {
-                            sg.out[(long long)lane * sg.out_bs + (long long)cur_pos * sg.pos_stride + (n - sg.n_begin)] = v;
-                            // K/V cache rows are read by LATER tokens through plain loads: order them before this thread's next tagged
-                            // store (the one of the following phase; this token's were issued above)
-                            __threadfence();
-                        }
-                    }
-                }
+                if (TRACE && mp.trace != nullptr && step == mp.trace_step && cta == mp.trace_cta) tr = mp.trace + (long long)pi * 16;
+                m3_gemv_phase<NB>(mp, ph2, sm, mapd, mapf, pl, cta, tid, g_idx, pi & 1, in_tag, out_tag, cur_pos, err, tr);
                 ++g_idx;
             } else if (ph.kind == 1) {
                 const DecAttnParams& a = ph.a;
@@ -896,22 +998,29 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
                     const int slot = a.row_slot ? sm.ctrl[4 + r] : r;
                     // K/V of the cache first (they do not depend on this token's phases), q and the appended row are polled inside
                     decode_attention_load<M2_WARPS>(a, s, h, r, slot, L, P, tid, areg);
+                    unsigned long long* tr = nullptr;
+                    if (TRACE && mp.trace != nullptr && step == mp.trace_step && cta == mp.trace_cta && u == cta) tr = mp.trace + (long long)pi * 16;
+                    if (tr && tid == 0) tr[1] = (unsigned long long)clock64();
                     m2_attention_unit(a, mp.ll, is_self, s, h, r, slot, L, P, in_tag, out_tag, sm.u.attn.sc, sm.u.attn.red, sm.u.attn.stat, sm.u.attn.qs,
-                                      sm.u.attn.kns, sm.u.attn.vns, tid, areg, err);
-                    if (a.n_splits > 1 && s == 0) { __syncthreads(); m2_attention_merge(a, mp.ll, h, r, out_tag, sm.u.attn.sc, tid, err); }
+                                      sm.u.attn.kns, sm.u.attn.vns, tid, areg, err, tr);
+                    if (tr && tid == 0) tr[5] = (unsigned long long)clock64();
+                    if (a.n_splits > 1 && s == 0) { __syncthreads(); m2_attention_merge(a, mp.ll, h, r, out_tag, sm.u.attn.sc, tid, err); if (tr && tid == 0) tr[6] = (unsigned long long)clock64(); }
                     __syncthreads();
                 }
             } else {
                 if (cta < sm.sample_params.cfg->B) {
-                    if (tid == 0) { sm.sample_params.ll_in_tag = in_tag; sm.sample_params.ll_out_tag = out_tag; }
+                    if (tid == 0) {
+                        sm.sample_params.ll_in_tag = in_tag; sm.sample_params.ll_out_tag = out_tag;
+                        sm.sample_params.trace = (TRACE && mp.trace != nullptr && step == mp.trace_step && cta == mp.trace_cta) ? mp.trace + (long long)pi * 16 : nullptr;
+                    }
                     __syncthreads();
-                    sample_body(sm.sample_params, cta, sm.u.sample);
+                    sample_body<M2_THREADS>(sm.sample_params, cta, sm.u.sample);
                 }
             }
-            if (!(ph.kind == 0 && MODE == 1)) {           // (the K-split GEMV phase ends with its own barrier, before its epilogue)
+            if (ph.kind != 0) {                           // (a GEMV phase ends with its own barrier, before its epilogue)
                 asm volatile("cp.async.wait_all;" ::: "memory");
-                __syncthreads();                          // xs / attention scratch free for the next phase; the next descriptor has landed
-                M2_TRACE(3);
+                __syncthreads();                          // attention / selection scratch free for the next phase; the next descriptor has landed
+                M2_TRACE(8);
             }
             cur = nxt;
         }
@@ -934,9 +1043,9 @@ int mega2_set_debug(int bits) {
     return 0;
 }
 
-template <int NB, bool TRACE, int MODE>
+template <int NB, bool TRACE>
 static const void* m2_configure() {
-    const void* fn = (const void*)decode_megakernel_ll<NB, TRACE, MODE>;
+    const void* fn = (const void*)decode_megakernel_ll<NB, TRACE>;
     static bool done = false;
     if (!done) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega2_smem_bytes()) != cudaSuccess) return nullptr;
@@ -952,12 +1061,7 @@ int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream) {
     MB_REQUIRE(mp.n_phases <= 126, "tag layout holds at most 126 phases per token");
     MB_REQUIRE(mp.d_model <= 1024, "residual scratch holds d_model <= 1024");
     const bool tr = mp.trace != nullptr, one = mp.rows == 1;
-    const void* fn = nullptr;
-    if (mp.gemv_mode == 1) {
-        fn = tr ? (one ? m2_configure<1, true, 1>() : m2_configure<2, true, 1>()) : (one ? m2_configure<1, false, 1>() : m2_configure<2, false, 1>());
-    } else {
-        fn = tr ? (one ? m2_configure<1, true, 0>() : m2_configure<2, true, 0>()) : (one ? m2_configure<1, false, 0>() : m2_configure<2, false, 0>());
-    }
+    const void* fn = tr ? (one ? m2_configure<1, true>() : m2_configure<2, true>()) : (one ? m2_configure<1, false>() : m2_configure<2, false>());
     MB_REQUIRE(fn != nullptr, "dataflow megakernel does not fit on an SM");
     Mega2Params p = mp;
     void* args[] = {&p};
@@ -970,7 +1074,7 @@ int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream) {
 // Limits of the K-split GEMV mapping for one phase (checked on the host when the phase table is built)
 bool mega2_ksplit_ok(int N, int K, int rows, int grid) {
     const int K4 = K >> 2, rpc = (N + grid - 1) / grid;
-    if ((K & 3) || K4 > 2 * M2_THREADS) return false;
+    if ((K & 3) || K4 > M3_NS * M2_THREADS) return false;
     const bool grouped = (K4 & 31) == 0 && K4 <= 256;
     const int G = grouped ? M2_THREADS / K4 : 1;
     return (rpc + G - 1) / G <= M3_SLOTS && rpc <= M3_ROWS && rpc * rows <= 64;

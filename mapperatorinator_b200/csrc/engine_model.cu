@@ -74,7 +74,8 @@ struct mb200_model {
     std::map<std::tuple<int, int, int, int>, int> prefill_seen;                                   // (rows, B, P, position rule)
     std::map<std::tuple<int, int, int, int>, std::pair<cudaGraphExec_t, long long>> prefill_graphs;   // -> graph + node count
     // persistent megakernel path
-    int use_mega = 3;                   // 0 = CUDA-graph replay per token, 1 = grid-barrier megakernel, 2 = dataflow (tagged-pair) megakernel, 3 = dataflow + K-split GEMV phases
+    int trace_cta = 0;                  // CTA whose phases the dataflow megakernel's TRACE instantiation stamps
+    int use_mega = 2;                   // 0 = CUDA-graph replay per token, 1 = grid-barrier megakernel, 2 = dataflow (tagged-pair) megakernel
     DevBuf ll_arena;                    // exchange buffers of the dataflow megakernel (rows <= 2)
     MegaLL ll{};
     size_t ll_bytes = 0;
@@ -733,6 +734,18 @@ static int run_megakernel2(mb200_model* m, int rows, int B, int n_splits_self, i
                 else if (sg.out == dh) q.out_sel[sgi] = LL_H;
                 else if (sg.out == dlog) q.out_sel[sgi] = LL_LOGITS;
                 else MB_REQUIRE(false, "dataflow megakernel: unknown GEMV output buffer");
+                const int os = q.out_sel[sgi];
+                const unsigned long long* ob = os == LL_X ? m->ll.x : os == LL_H ? m->ll.h : os == LL_Q ? m->ll.q : os == LL_LOGITS ? m->ll.logits : m->ll.kvnew;
+                q.out_off[sgi] = (long long)(ob - m->ll.x) + (os == LL_V ? m->cfg.d_model : 0);
+                q.out_rs[sgi] = os == LL_X ? m->ll.x_rep : (os == LL_H ? m->ll.h_rep : 0);
+                q.out_bw[sgi] = os == LL_H ? g.N : (os == LL_K || os == LL_V ? 2 * m->cfg.d_model : (os == LL_LOGITS ? m->cfg.vocab_size_out : m->cfg.d_model));
+            }
+            {
+                const unsigned long long* ib = q.in_sel == LL_H ? m->ll.h : (q.in_sel == LL_ATT ? m->ll.att : m->ll.x);
+                q.in_off = (long long)(ib - m->ll.x);
+                q.in_rs = q.in_sel == LL_H ? m->ll.h_rep : m->ll.x_rep;
+                const int rpc = (g.N + m->num_sms - 1) / m->num_sms;
+                q.n_active = (g.N + rpc - 1) / rpc;
             }
         }
         DevBuf* buf = new DevBuf();
@@ -750,16 +763,8 @@ static int run_megakernel2(mb200_model* m, int rows, int B, int n_splits_self, i
     mp.sample.ll_logits = m->ll.logits; mp.sample.ll_x_out = m->ll.x; mp.sample.ll_hdr = m->ll.hdr; mp.sample.ll_err = mp.error_flag;
     mp.sample.ll_reps = m->ll.reps; mp.sample.ll_x_rep = m->ll.x_rep;
     mp.max_steps = max_steps; mp.row_slot = m->g_rowslot.as<int>(); mp.x_in = m->d_x.as<float>();
-    mp.rows = rows; mp.d_model = m->cfg.d_model; mp.V = m->cfg.vocab_size_out; mp.ffn_dim = m->cfg.ffn_dim;
+    mp.rows = rows; mp.d_model = m->cfg.d_model; mp.V = m->cfg.vocab_size_out; mp.ffn_dim = m->cfg.ffn_dim; mp.trace_cta = m->trace_cta;
     mp.trace = m->mega_trace.p ? m->mega_trace.as<unsigned long long>() : nullptr; mp.trace_step = 8;
-    {   // K-split GEMV phases when every projection of this model fits the thread mapping, else the row-per-warp form
-        const auto& c = m->cfg;
-        const int G = m->num_sms;
-        const bool ks = mega2_ksplit_ok(3 * c.d_model, c.d_model, rows, G) && mega2_ksplit_ok(c.d_model, c.d_model, rows, G) &&
-                        mega2_ksplit_ok(c.ffn_dim, c.d_model, rows, G) && mega2_ksplit_ok(c.d_model, c.ffn_dim, rows, G) &&
-                        mega2_ksplit_ok(c.vocab_size_out, c.d_model, rows, G);
-        mp.gemv_mode = (m->use_mega == 3 && ks) ? 1 : 0;
-    }
     if (!m->mega_ev[0]) { MB_CUDA_CHECK(cudaEventCreate(&m->mega_ev[0])); MB_CUDA_CHECK(cudaEventCreate(&m->mega_ev[1])); }
     MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag + 2, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
     MB_CUDA_CHECK(cudaEventRecord(m->mega_ev[0], st));
@@ -905,7 +910,14 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
 
     // ---- token loop, persistent path: every remaining token in ONE cooperative launch ----
     if (mega_eligible(m, rows) && gp->max_length - (P + 1) > 0) {
-        if (m->use_mega >= 2) MB_TRY(run_megakernel2(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
+        bool dataflow = m->use_mega >= 2;
+        if (dataflow) {     // every projection of this model must fit the K-split thread mapping, else the grid-barrier kernel takes the call
+            const int G = m->num_sms;
+            dataflow = mega2_ksplit_ok(3 * c.d_model, c.d_model, rows, G) && mega2_ksplit_ok(c.d_model, c.d_model, rows, G) &&
+                       mega2_ksplit_ok(c.ffn_dim, c.d_model, rows, G) && mega2_ksplit_ok(c.d_model, c.ffn_dim, rows, G) &&
+                       mega2_ksplit_ok(c.vocab_size_out, c.d_model, rows, G);
+        }
+        if (dataflow) MB_TRY(run_megakernel2(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
         else MB_TRY(run_megakernel(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
         MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
         MB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1007,6 +1019,7 @@ extern "C" int mb200_model_set_option(mb200_model* m, const char* name, int valu
     }
     if (!strcmp(name, "mega")) { m->use_mega = value; return 0; }
     if (!strcmp(name, "ll_sleep")) return mega2_set_poll_sleep(value);
+    if (!strcmp(name, "trace_cta")) { m->trace_cta = value; return 0; }
     if (!strcmp(name, "ll_debug")) return mega2_set_debug(value);
     if (!strcmp(name, "ll_reps")) {
         MB_REQUIRE(value >= 1 && value <= MEGA_LL_MAX_REPS && value * 2 <= 32, "ll_reps must be in [1, 16]");

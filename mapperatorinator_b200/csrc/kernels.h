@@ -215,6 +215,7 @@ struct SampleParams {
     unsigned long long* ll_x_out; unsigned long long* ll_hdr; unsigned ll_out_tag;
     int ll_reps; long long ll_x_rep;                // replicas of the residual-stream buffer and their stride (see MegaLL)
     int* ll_err;
+    unsigned long long* trace;                      // tools/mega3_trace.py: clock64 stamps inside the selection phase (null in production)
 };
 int launch_sample(const SampleParams& p, int B, cudaStream_t stream, bool pdl);
 
@@ -271,6 +272,11 @@ struct Mega2Phase {
     int out_sel[3];                               // per output segment: which exchange buffer receives the tagged copy (LL_NONE = plain only)
     int res_xraw;                                 // epilogue adds the residual from the raw x this CTA staged at the last LL_X input
     int plain_out[3];                             // per segment: also store plainly through seg.out (the K/V cache)
+    // host-resolved exchange-buffer geometry, in pairs relative to MegaLL::x (the start of the arena), so the kernel's prologue is a
+    // few adds instead of chains of shared-memory loads and selects
+    long long in_off, in_rs;                      // GEMV input buffer and its replica stride
+    int n_active;                                 // CTAs that own output rows in this GEMV phase: ceil(N / rows-per-CTA)
+    long long out_off[3], out_rs[3], out_bw[3];   // per segment: tagged output buffer (incl. the V half of kvnew), replica stride (0 = one copy), pairs per decoder row
 };
 struct Mega2Params {
     const Mega2Phase* phases; int n_phases;
@@ -282,8 +288,7 @@ struct Mega2Params {
     const int* row_slot;
     const float* x_in;                            // [rows][d] plain residual stream left by the prefill's selection kernel
     int rows, d_model, V, ffn_dim;
-    unsigned long long* trace; int trace_step;    // optional [4 CTAs][n_phases][4] clock64 stamps (tools/mega2_trace.py)
-    int gemv_mode;                                // 0 row-per-warp GEMV phases (shared-memory staging), 1 K-split GEMV phases (decode_mega2.cu, m3_*)
+    unsigned long long* trace; int trace_step, trace_cta;    // optional [n_phases][16] clock64 stamps of one CTA (tools/mega3_trace.py)
 };
 size_t mega2_smem_bytes();
 int launch_megakernel2(const Mega2Params& mp, int grid, cudaStream_t stream);

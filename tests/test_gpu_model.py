@@ -53,10 +53,10 @@ def test_teacher_forced_logits_left_padded(tiny, gen_gold):
     assert np.allclose(out.numpy()[:, ::3, ::37][r3], g[r3], rtol=1e-3, atol=3e-4)
 
 
-MEGA_MODE = {"megakernel": 1, "dataflow": 2, "dataflow_ksplit": 3, "graph": 0, "graph_pdl": 0}
+MEGA_MODE = {"megakernel": 1, "dataflow": 2, "graph": 0, "graph_pdl": 0}
 
 
-@pytest.mark.parametrize("path", ["dataflow_ksplit", "dataflow", "megakernel", "graph", "graph_pdl"])
+@pytest.mark.parametrize("path", ["dataflow", "megakernel", "graph", "graph_pdl"])
 @pytest.mark.parametrize("case", list(cases.generate_cases()))
 def test_greedy_generate_bit_exact(tiny, layout, gen_gold, case, path):
     """Every token-loop driver (dataflow megakernel = tagged-pair exchange, no grid barrier; grid-barrier megakernel; CUDA-graph
@@ -75,7 +75,7 @@ def test_greedy_generate_bit_exact(tiny, layout, gen_gold, case, path):
     try:
         got, gstats = model_generate(model, layout, dict(mk), dict(gk))
     finally:
-        model.engine.set_option("mega", 3)
+        model.engine.set_option("mega", 2)
         model.engine.set_option("pdl", 0)
     assert got.shape == want.shape, (got.shape, want.shape)
     if not torch.equal(got, want):
@@ -85,7 +85,7 @@ def test_greedy_generate_bit_exact(tiny, layout, gen_gold, case, path):
     assert np.array_equal(got.numpy(), gen_gold[f"{flavour}/{case}/ids"]), "differs from the reference fixture"
 
 
-@pytest.mark.parametrize("path", ["dataflow_ksplit", "dataflow", "megakernel", "graph"])
+@pytest.mark.parametrize("path", ["dataflow", "megakernel", "graph"])
 @pytest.mark.parametrize("case", list(cases.long_context_cases()))
 def test_greedy_generate_long_context(tiny, layout, gen_gold, case, path):
     """Contexts beyond 128 tokens switch the self-attention cache to 64-key splits merged by the last-arriving split (3 splits at
@@ -103,7 +103,7 @@ def test_greedy_generate_long_context(tiny, layout, gen_gold, case, path):
     try:
         got, _ = model_generate(model, layout, dict(mk), dict(gk))
     finally:
-        model.engine.set_option("mega", 3)
+        model.engine.set_option("mega", 2)
     assert got.shape == want.shape
     if not torch.equal(got, want):
         r, c = (got != want).nonzero()[0].tolist()
