@@ -209,6 +209,10 @@ int mb200_op_layernorm(const float* x, float* y, const float* w, const float* b,
 int mb200_op_attention(const float* q, const float* k, const float* v, float* o, int32_t B, int32_t H, int32_t Tq, int32_t Tk,
                        float scale, int32_t mask_mode, int32_t q_pos0, const uint8_t* key_valid, int32_t band,
                        const uint8_t* dense_mask, void* cuda_stream);
+/* Tuning / tests: tensor-core (tcgen05, 3xTF32) flash attention on or off, and the minimum number of queries for which it is used
+   (attention_tc.cu; replaces the SIMT kernel for the encoder self-attention of HF modeling_whisper.py:286-358 and the DiT band of
+   osu_diffusion/utils/models.py:145-151). */
+int mb200_set_attention_tc(int32_t enabled, int32_t min_queries);
 
 #ifdef __cplusplus
 }

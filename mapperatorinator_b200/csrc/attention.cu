@@ -171,9 +171,10 @@ __global__ void __launch_bounds__(256) attention_kernel(AttentionParams p) {
 
 }  // namespace
 
-int launch_attention(const AttentionParams& p, cudaStream_t stream) {
+int launch_attention(const AttentionParams& p, cudaStream_t stream, AttnCtx* ctx) {
     MB_REQUIRE(p.q_ld % 4 == 0 && p.k_ld % 4 == 0 && p.v_ld % 4 == 0 && p.o_ld % 4 == 0, "attention strides must be multiples of 4");
     if (p.B <= 0 || p.Tq <= 0) return 0;
+    if (attn_tc_eligible(p, ctx)) return launch_attention_tc(p, stream, ctx);
     static bool configured = false;
     const int smem_bytes = 4 * HD * LDS_ * (int)sizeof(float);
     if (!configured) {

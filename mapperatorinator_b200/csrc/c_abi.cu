@@ -100,5 +100,17 @@ extern "C" int mb200_op_attention(const float* q, const float* k, const float* v
     a.o = o; a.o_ld = D; a.o_bs = (long long)Tq * D;
     a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.scale = scale; a.mask_mode = mask_mode; a.q_pos0 = q_pos0;
     a.key_valid = key_valid; a.key_valid_ld = Tk; a.band = band; a.dense = dense_mask; a.kv_slot = nullptr;
-    return launch_attention(a, (cudaStream_t)stream);
+    static AttnCtx op_ctx;                    // scratch of this kernel-level test entry point
+    const int rc = launch_attention(a, (cudaStream_t)stream, &op_ctx);
+    if (rc) return rc;
+    if (attn_tc_eligible(a, &op_ctx)) {       // surface a pipeline time-out of the tensor-core path as an error of the call
+        MB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+        MB_REQUIRE(op_ctx.error() == 0, "tensor-core attention: a pipeline wait timed out");
+    }
+    return 0;
+}
+// tuning / tests: minimum query count for the tensor-core attention path (0 disables it)
+extern "C" int mb200_set_attention_tc(int32_t enabled, int32_t min_queries) {
+    g_attn_tc_enabled = enabled; g_attn_tc_min_t = min_queries;
+    return 0;
 }

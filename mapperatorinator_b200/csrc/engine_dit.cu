@@ -200,6 +200,7 @@ struct mb200_dit {
     bool use_graph = true;
     float graph_cfg_scale = 0.f; const void* graph_noise = nullptr; const void* graph_mods = nullptr;   // what the cached graphs baked
     GemmCtx gemm;
+    AttnCtx attn;                       // tensor-core attention scratch (head-major tf32 copies of q | k | v^T)
 };
 
 extern "C" int mb200_dit_create(mb200_dit** out, const mb200_dit_config* cfg) {
@@ -219,6 +220,7 @@ extern "C" void mb200_dit_destroy(mb200_dit* d) {
     for (auto& g : d->step_graphs) cudaGraphExecDestroy(g.second.first);
     if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
     d->gemm.destroy();
+    d->attn.destroy();
     delete d;
 }
 
@@ -302,6 +304,8 @@ extern "C" int mb200_dit_finalize(mb200_dit* dd) {
         const size_t K0 = (size_t)c.in_channels * c.pos_freq_dim + c.context_size;
         MB_TRY(dd->gemm.reserve((size_t)64 << 20, R * std::max((size_t)d * c.mlp_ratio, K0) * 8 + 1024));
         dd->gemm.frozen = true;
+        MB_TRY(dd->attn.reserve(attn_tc_workspace_bytes(std::max(2, c.max_batch), c.heads, c.max_seq_len, c.max_seq_len)));
+        dd->attn.frozen = true;
     }
     dd->host_w.clear();
     dd->finalized = true;
@@ -392,7 +396,7 @@ int dit_forward(mb200_dit* dd, const float* xstate, const float* cctx, int N, in
         a.o = dd->att.f(); a.o_ld = d; a.o_bs = (long long)T * d;
         a.B = N; a.H = c.heads; a.Tq = T; a.Tk = T; a.scale = 1.f;
         a.mask_mode = mask ? mask->mask_mode : MASK_NONE; a.band = mask ? mask->band : 0; a.dense = mask ? mask->dense_mask : nullptr;
-        MB_TRY(launch_attention(a, st));
+        MB_TRY(launch_attention(a, st, &dd->attn));
         {
             GemmParams g = gb(dd->att.f(), d, w.out_w, d, dd->x.f(), d, w.out_b, R, d, d);
             g.gate = mod + 2 * d; g.gate_ld = 6 * d; g.gate_rpb = T; g.R = plain_map(dd->x.f(), d);

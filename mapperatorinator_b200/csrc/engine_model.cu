@@ -87,6 +87,7 @@ struct mb200_model {
     cudaEvent_t mega_ev[2] = {nullptr, nullptr};
     double mega_ms = 0.0; long long mega_launches = 0, mega_tokens = 0;   // CUDA-event time of every megakernel launch
     std::map<std::pair<int, int>, std::pair<DevBuf*, int>> mega_phases;   // (rows, n_splits_self) -> device phase table
+    AttnCtx attn;                       // tensor-core attention scratch of the encoder (head-major tf32 copies of q | k | v^T)
     GemmCtx gemm;                       // this engine's GEMM scratch: split-K planes, tf32 activation copies, weight mirrors, error flag
 
     int d() const { return cfg.d_model; }
@@ -175,6 +176,7 @@ extern "C" void mb200_model_destroy(mb200_model* m) {
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
     for (auto& g : m->prefill_graphs) cudaGraphExecDestroy(g.second.first);
     m->gemm.destroy();
+    m->attn.destroy();
     for (auto& kv : m->mega_phases) delete kv.second.first;
     for (auto& kv : m->mega2_phases) delete kv.second.first;
     for (auto& e : m->mega_ev) if (e) cudaEventDestroy(e);
@@ -307,6 +309,8 @@ extern "C" int mb200_model_finalize(mb200_model* m) {
         m->gemm.num_sms = std::max(1, m->num_sms_phys);
         MB_TRY(m->gemm.reserve((size_t)64 << 20, a_floats * 8 + 1024));
         m->gemm.frozen = true;
+        MB_TRY(m->attn.reserve(attn_tc_workspace_bytes((int)chunk, c.heads, c.src_seq_len / 2, c.src_seq_len / 2)));
+        m->attn.frozen = true;
     }
 
     // ---- resident state ----
@@ -407,7 +411,7 @@ static int encode_chunk(mb200_model* m, const float* pcm, int n, int slot_begin,
         a.v = qkv + 2 * d; a.v_ld = 3 * d; a.v_bs = a.q_bs;
         a.o = att; a.o_ld = d; a.o_bs = (long long)T * d;
         a.B = n; a.H = H; a.Tq = T; a.Tk = T; a.scale = 1.f; a.mask_mode = MASK_NONE;
-        MB_TRY(launch_attention(a, st));
+        MB_TRY(launch_attention(a, st, &m->attn));
         {
             GemmParams g = gemm_base(plain_map(att, d), w.wo, d, plain_map(x, d), w.bo, rows, d, d);
             g.R = plain_map(x, d);
@@ -720,6 +724,7 @@ static int run_megakernel2(mb200_model* m, int rows, int B, int n_splits_self, i
             Mega2Phase& q = p2[i];
             q = Mega2Phase{};
             q.base = phases[i];
+            if (phases[i].kind == 1 && phases[i].a.fixed_len == 0 && phases[i].a.n_splits == 1) q.base.a.chunk = 256;   // one 256-key unit per head
             if (phases[i].kind != 0) continue;
             const GemvParams& g = phases[i].g;
             q.in_sel = g.xmode == X_LAYERNORM ? LL_X : (g.x == datt ? LL_ATT : (g.x == dh ? LL_H : LL_NONE));
@@ -917,6 +922,8 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
                        mega2_ksplit_ok(c.ffn_dim, c.d_model, rows, G) && mega2_ksplit_ok(c.d_model, c.ffn_dim, rows, G) &&
                        mega2_ksplit_ok(c.vocab_size_out, c.d_model, rows, G);
         }
+        // (the dataflow kernel's attention unit can hold 256 keys, but ONE 146-key unit per head measured slower than three 64-key units +
+        //  merge — 365 vs 344 us / token: its V rows beyond the first 64 keys are fetched inside the PV loop — so the split rule stays)
         if (dataflow) MB_TRY(run_megakernel2(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
         else MB_TRY(run_megakernel(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
         MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));

@@ -88,7 +88,21 @@ struct AttentionParams {
     const unsigned char* dense;    // MASK_DENSE: [Tq, Tk] 1 = blocked
     const int* kv_slot;            // optional: K/V batch index of batch row b (cross attention over resident encoder slots)
 };
-int launch_attention(const AttentionParams& p, cudaStream_t stream);
+// Per-engine scratch of the tensor-core attention path (attention_tc.cu): head-major tf32 hi / lo copies of q, k and v^T.
+struct AttnCtx {
+    void* ws = nullptr; size_t ws_bytes = 0;
+    int* err = nullptr;                              // device flag: 0 fine, 5 = a pipeline wait timed out
+    bool frozen = false;                             // set once a CUDA graph holds the workspace address
+    int reserve(size_t bytes);                       // grow-only; fails loudly when frozen and too small
+    int error();
+    void destroy();
+};
+extern int g_attn_tc_enabled, g_attn_tc_min_t;
+size_t attn_tc_workspace_bytes(int B, int H, int Tq, int Tk);
+bool attn_tc_eligible(const AttentionParams& p, const AttnCtx* ctx);
+int launch_attention_tc(const AttentionParams& p, cudaStream_t stream, AttnCtx* ctx);
+// ctx != null and an eligible problem (no dense mask, no kv_slot gather, enough queries): tcgen05 flash attention; else the fp32 SIMT kernel
+int launch_attention(const AttentionParams& p, cudaStream_t stream, AttnCtx* ctx = nullptr);
 
 // ---- slider.cu: slider end-point recompute of the diffusion denoised_fn (diffusion_pipeline.py:203-222) -------------------
 struct SliderSet {                 // device arrays describing the sliders that lie fully inside the current chunk

@@ -104,6 +104,39 @@ def test_attention_masks(Tq, Tk, mode):
     assert torch.allclose(out, ref, rtol=2e-5, atol=2e-5), (out - ref).abs().max()
 
 
+@pytest.mark.parametrize("Tq,Tk,mode,scale", [(1024, 1024, "band", 0.125), (512, 512, "none", 1.0), (130, 700, "none", 0.3),
+                                              (333, 333, "causal", 1.0), (260, 260, "band", 1.0)])
+def test_attention_tensor_cores(Tq, Tk, mode, scale):
+    """tcgen05 flash attention (3xTF32 for Q.K^T and P.V, softmax state in the row's own thread) vs an fp64 reference, and against the
+    fp32 SIMT kernel it replaces: DiT shape (T = 1024, +-128 band), encoder shape (T = 512), ragged tiles, causal with left padding."""
+    from mapperatorinator_b200 import _lib, ops
+    lib = _lib.load()
+    B, H = 2, 3
+    g = _g(Tq * 3 + Tk)
+    q, k, v = (torch.randn(B, t, H * 64, generator=g) for t in (Tq, Tk, Tk))
+    r, c = torch.arange(Tq)[:, None], torch.arange(Tk)[None, :]
+    allowed = torch.ones(B, Tq, Tk, dtype=torch.bool)
+    kw = {}
+    if mode == "causal":
+        kvalid = torch.ones(B, Tk, dtype=torch.uint8)
+        kvalid[1, :9] = 0
+        allowed = (c <= r)[None] & kvalid.bool()[:, None, :]
+        kw = dict(key_valid=kvalid.cuda())
+    elif mode == "band":
+        allowed = ((r >= c - 128) & (r < c + 128))[None].expand(B, -1, -1)
+        kw = dict(band=128)
+    ref = _ref_attn((q * scale).double(), k.double(), v.double(), H, allowed).float()
+    try:
+        _lib.check(lib.mb200_set_attention_tc(1, 64))
+        out_tc = ops.attention(q.cuda(), k.cuda(), v.cuda(), H, scale, mode, 0, **kw).cpu()
+        _lib.check(lib.mb200_set_attention_tc(0, 256))
+        out_simt = ops.attention(q.cuda(), k.cuda(), v.cuda(), H, scale, mode, 0, **kw).cpu()
+    finally:
+        _lib.check(lib.mb200_set_attention_tc(1, 256))
+    assert torch.allclose(out_tc, ref, rtol=2e-5, atol=2e-5), (out_tc - ref).abs().max()
+    assert torch.allclose(out_tc, out_simt, rtol=2e-5, atol=2e-5), (out_tc - out_simt).abs().max()
+
+
 @pytest.mark.parametrize("flavour", ["nnAudio", "torchaudio", "torchaudio_log_reflect"])
 @pytest.mark.parametrize("n_samples", [130944, 128 * 37])
 def test_mel_vs_oracle(flavour, n_samples):
