@@ -2,7 +2,7 @@
 """bench.py — event tokens/sec of the Mapperatorinator inference hot path on B200 (contract: see README "Measurement").
 
 Workload (BASELINE.json configs[1] + configs[2], SURVEY §8d rows 2a + 3): osuT5 v29 dimensions (whisper-small, 213 M params,
-fp32, seeded random weights), one 180 s synthetic 16 kHz song -> 211 sequential windows (stride 13 094 samples), greedy decode,
+fp32, seeded random weights), one 180 s synthetic song as 44.1 kHz 16-bit stereo PCM -> GPU ingest (resample to 16 kHz, mono, peak-normalise) -> 211 sequential windows (stride 13 094 samples), greedy decode,
 `min_new_tokens = 64`, `max_length = P + 64` (random weights have no EOS behaviour, so the token budget is pinned:
 211 x 64 = 13 504 event tokens per step), real look-back / look-ahead EOS sets and logits-processor chain, prompt =
 16 conditioning ids + SOS + ctx_sos(MAP) (+ the last 32 generated ids of the previous window -> sequential dependency);
@@ -10,10 +10,11 @@ THEN the osu_diffusion stage the metric names ("mel+T5+DiT"): DiT-B (131 M param
 points -> chunks [0:1024] and [768:1500] (diffusion_pipeline.py:276-284), 100 denoising steps each, CFG pair, +-128 band mask.
 
 A "step" = one full song (decode + position refinement).
-  value : tokens/s with the PCM windows and the DiT inputs already resident in HBM (engine path: one batched mel+encoder pass
-          over all windows, cross-K/V resident, sequential prefill + token loop per window, fused on-device 100-step loops),
+  value : tokens/s with the song's file PCM (int16) and the DiT inputs already resident in HBM (engine path: GPU audio ingest + device
+          segmentation, one batched mel+encoder pass over all windows, cross-K/V resident, sequential prefill + token loop per window, fused on-device 100-step loops),
           CUDA-event timed.  `value_decode_only` = the same without the DiT stage (round-1's number).
-  e2e   : the same song through the reference-facing calls with HOST tensors: `server.model_generate(model, tokenizer,
+  e2e   : the same song through the reference-facing calls with HOST tensors: `audio.load_pcm` + `pipeline.segment` where the reference
+          runs `load_audio_file` + `Preprocessor.segment` (host PCM in, host windows out), `server.model_generate(model, tokenizer,
           model_kwargs, generate_kwargs)` once per window (pinned PCM in, CPU LongTensor out, encoder re-run per call as the
           reference does) and `diffusion.sample_sequence` (pinned seq_x / seq_c / y in, CPU positions out) — H2D, D2H inside
           the timed region.
@@ -40,7 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from mapperatorinator_b200 import TokenLayout, dit_b_config, v29_model_config  # noqa: E402
-from mapperatorinator_b200.pipeline import gather_token_streams, segment  # noqa: E402
+from mapperatorinator_b200.pipeline import gather_token_streams, segment, segment_device  # noqa: E402
 from mapperatorinator_b200.weights import init_dit_state_dict, init_model_state_dict  # noqa: E402
 
 SONG_SECONDS = 180.0
@@ -61,6 +62,33 @@ def synth_song(seed: int, seconds: float = SONG_SECONDS, sr: int = 16000) -> np.
     clicks[(np.arange(0, seconds, 0.5) * sr).astype(int)] = 1.0
     x = x + np.convolve(clicks, np.hanning(64), mode="same") + rng.normal(0, 0.01, n)
     return (x / np.abs(x).max()).astype(np.float32)
+
+
+FILE_RATE, MODEL_RATE = 44100, 16000
+
+
+def synth_song_pcm(seed: int, seconds: float = SONG_SECONDS) -> np.ndarray:
+    """The song as an audio FILE holds it (BASELINE: synthetic 44.1 kHz audio): interleaved 16-bit stereo PCM, int16 [n, 2] — the same
+    recipe as `synth_song` at 44.1 kHz, the right channel a slightly attenuated, phase-shifted copy."""
+    rng = np.random.default_rng(seed)
+    n = int(seconds * FILE_RATE)
+    t = np.arange(n) / FILE_RATE
+    ph = [rng.uniform(0, 2 * np.pi) for _ in range(8)]
+    left = sum(np.sin(2 * np.pi * f * t + p) for f, p in zip(np.geomspace(55, 7000, 8), ph)) / 8
+    right = sum(np.sin(2 * np.pi * f * t + p + 0.3) for f, p in zip(np.geomspace(55, 7000, 8), ph)) / 8 * 0.9
+    clicks = np.zeros(n)
+    clicks[(np.arange(0, seconds, 0.5) * FILE_RATE).astype(int)] = 1.0
+    clicks = np.convolve(clicks, np.hanning(176), mode="same")
+    noise = rng.normal(0, 0.01, (n, 2))
+    x = np.stack([left + clicks, right + clicks], 1) + noise
+    return np.clip(np.round(x / np.abs(x).max() * 30000.0), -32768, 32767).astype(np.int16)
+
+
+def oracle_windows(seed: int, cfg):
+    """CPU-side view of the same song for the checks / the CPU arm: the reference's ingest arithmetic (oracle.audio.ingest_reference =
+    audioop.ratecv + tomono + peak normalisation, data_utils.py:80-101) and `Preprocessor.segment`."""
+    from oracle import audio as audio_oracle
+    return segment(audio_oracle.ingest_reference(synth_song_pcm(seed), FILE_RATE, MODEL_RATE), cfg)[0]
 
 
 def prompt_for(i: int, streams) -> list:
@@ -134,7 +162,7 @@ class ClockSampler:
 
 
 def workload_config(n_windows: int, dit: bool, songs_per_gpu: int = 1) -> dict:
-    cfg = {"workload": "osuT5 v29 full-song inference, 180 s synthetic 16 kHz audio, sequential sliding windows (configs[1], SURVEY 8d 2a)"
+    cfg = {"workload": "osuT5 v29 full-song inference, 180 s synthetic 44.1 kHz 16-bit stereo audio -> GPU ingest to 16 kHz mono (data_utils.py:80-101) -> sequential sliding windows (configs[1], SURVEY 8d 2a)"
                        + (" + osu_diffusion DiT-B 100-step position refinement (configs[2], SURVEY 8d 3)" if dit else ""),
            "windows": n_windows, "new_tokens_per_window": NEW_TOKENS, "decode": "greedy, min_new_tokens=64", "batch": songs_per_gpu,
            "weights": "seeded random init, whisper-small dims (213M) + DiT-B (131M), fp32", "songs_per_gpu_per_step": songs_per_gpu,
@@ -196,7 +224,7 @@ def run_reference(args, rank: int, world: int) -> None:
     cfg = v29_model_config()
     layout = TokenLayout.from_json(os.path.join(ROOT, "tests", "golden", "tokenizer_v29.json"))
     sd = init_model_state_dict(cfg, 0)
-    windows, _, _ = segment(synth_song(args.song_seed), cfg)
+    windows = oracle_windows(args.song_seed, cfg)
     n_windows = windows.shape[0]
     for _ in range(args.warmup):
         cpu_sample(args, cfg, layout, windows, n_windows, sd)
@@ -278,6 +306,7 @@ def main() -> None:
     from mapperatorinator_b200 import _lib
     from mapperatorinator_b200.diffusion import B200DiT, sample_sequence
     from mapperatorinator_b200.modeling import B200Mapperatorinator
+    from mapperatorinator_b200.audio import load_pcm
     from mapperatorinator_b200.pipeline import SongDecoder
     from mapperatorinator_b200.server import model_generate
     torch.cuda.set_device(local)
@@ -290,7 +319,10 @@ def main() -> None:
     S = max(1, args.songs_per_gpu)
     song_ids = [args.song_seed + rank * S + k for k in range(S)]      # rank r decodes songs song_seed + r*S .. + S-1
     song_id = song_ids[0]
-    songs = [segment(synth_song(sid), cfg)[0] for sid in song_ids]
+    # the song enters as its file holds it: 44.1 kHz 16-bit stereo PCM; ingest (resample + mono + normalise) runs on the GPU (audio.load_pcm)
+    pcm_host = [torch.from_numpy(synth_song_pcm(sid)).pin_memory() for sid in song_ids]
+    pcm_dev = [t.to(dev) for t in pcm_host]
+    songs = [segment_device(load_pcm(t, FILE_RATE, MODEL_RATE), cfg).cpu() for t in pcm_dev]
     if args.windows:
         songs = [w[:args.windows] for w in songs]
     windows = songs[0]
@@ -333,7 +365,8 @@ def main() -> None:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         for k in range(S):
-            song.encode_song(resident[k], slot_begin=k * n_windows)
+            w = segment_device(load_pcm(pcm_dev[k], FILE_RATE, MODEL_RATE), cfg)          # 44.1 kHz stereo int16 (resident) -> 16 kHz mono windows
+            song.encode_song(w[:n_windows], slot_begin=k * n_windows)
         ev[1].record()
         if S == 1:
             streams = [song.decode_windows(n_windows, prompt_for, lambda i: gen_kwargs(i, n_windows, 18 if i == 0 else 50))]
@@ -350,6 +383,9 @@ def main() -> None:
 
     def step_e2e():
         streams, toks = [[] for _ in range(S)], 0
+        for k in range(S):        # where the reference runs load_audio_file + Preprocessor.segment: host PCM in, host windows out
+            x = load_pcm(pcm_host[k], FILE_RATE, MODEL_RATE).cpu().numpy()
+            pinned[k].copy_(segment(x, cfg)[0][:n_windows])
         for i in range(n_windows):
             prompt = torch.tensor([prompt_for(i, streams[k]) for k in range(S)])
             ids, stats = model_generate(model, layout, dict(inputs=pinned[:, i], decoder_input_ids=prompt, decoder_attention_mask=prompt.ne(0)),
@@ -467,10 +503,14 @@ def main() -> None:
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu, oracle_check, dit_parity = None, None, None
+    cpu, oracle_check, dit_parity, ingest_parity = None, None, None, None
     if not args.no_cpu_baseline and world == 1:
         cores = args.cpu_threads or min(os.cpu_count() or 1, 16)
         torch.set_num_threads(cores)
+        cpu_windows = oracle_windows(song_id, cfg)[:n_windows]                # the reference's ingest arithmetic + Preprocessor.segment, on the CPU
+        ingest_parity = {"gpu_windows_equal_reference_ingest": bool(torch.equal(cpu_windows, windows)), "windows": int(n_windows),
+                         "samples_in": int(pcm_host[0].shape[0]), "file": "44.1 kHz 16-bit stereo", "model_rate": MODEL_RATE}
+        windows = cpu_windows
         ctoks, csecs, sample, info = cpu_sample(args, cfg, layout, windows, n_windows, sd, streams)
         cpu = {"value": ctoks / csecs, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample, **info}
         if args.oracle_check != "none":
@@ -499,8 +539,8 @@ def main() -> None:
                                      model_kwargs=mk, step_noise=noise.to(dev)).cpu()
             err = float((got - ref).abs().max())
             dit_parity = {"chunk_points": Tp, "steps": DIT_STEPS, "max_abs_err": err, "tolerance": 1e-3, "ok": bool(err <= 1e-3), "oracle_seconds": t_ref}
-    h2d = S * n_windows * cfg.samples_per_window * 4
-    d2h = S * n_windows * (50 + NEW_TOKENS) * 8
+    h2d = S * n_windows * cfg.samples_per_window * 4 + S * int(pcm_host[0].numel()) * 2      # per-window PCM + the file's int16 PCM for the ingest
+    d2h = S * n_windows * (50 + NEW_TOKENS) * 8 + S * 4 * int(lib.mb200_audio_out_frames(int(pcm_host[0].shape[0]), FILE_RATE, MODEL_RATE))      # token ids + the ingested signal
     if dit is not None:
         h2d += S * 4 * (2 * DIT_POINTS + dc.context_size * DIT_POINTS + 2 * DIT_CLASSES)
         d2h += S * 4 * 2 * DIT_POINTS
@@ -514,10 +554,10 @@ def main() -> None:
                 "api": "server.model_generate per window (host tensors in, CPU LongTensor out)"
                        + (" + diffusion.sample_sequence (host tensors in, CPU positions out)" if dit is not None else "")},
         "value_decode_only": tok_per_song * world / (decode_only_ms / 1000) if decode_only_ms > 0 else None,
-        "stages_ms_per_song": {**stage_ms, "note": "rank 0, resident arm, CUDA events: mel+encoder (all windows, batched) | prefill + token loop "
+        "stages_ms_per_song": {**stage_ms, "note": "rank 0, resident arm, CUDA events: audio ingest + mel+encoder (all windows, batched) | prefill + token loop "
                                                    "(all windows) | DiT refinement (2 chunks x 100 steps)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "self_consistency": consistency, "oracle_check": oracle_check,
-        "dit_parity": dit_parity, "pdl": bool(args.pdl), "tensor_cores": bool(args.tc), "song_seed": args.song_seed,
+        "dit_parity": dit_parity, "ingest_parity": ingest_parity, "pdl": bool(args.pdl), "tensor_cores": bool(args.tc), "song_seed": args.song_seed,
         "token_stream_sha1": hashlib.sha1(json.dumps(streams).encode()).hexdigest(),
         "token_stream_sha1_all_songs": hashlib.sha1(json.dumps(all_streams).encode()).hexdigest() if S > 1 else None}))
     if world > 1:

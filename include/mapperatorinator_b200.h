@@ -214,6 +214,17 @@ int mb200_op_attention(const float* q, const float* k, const float* v, float* o,
    osu_diffusion/utils/models.py:145-151). */
 int mb200_set_attention_tc(int32_t enabled, int32_t min_queries);
 
+/* ---- audio ingest ---------------------------------------------------------------------------------------------
+   Replaces the CPU tail of the reference's `load_audio_file` (osuT5/osuT5/dataset/data_utils.py:80-101, called by Preprocessor.load,
+   osuT5/osuT5/inference/preprocessor.py:39): pydub `set_frame_rate` (audioop.ratecv) -> `set_channels(1)` (audioop.tomono) -> float32 ->
+   `normalize_audio_samples` (:132-137).  File decoding (ffmpeg) stays with the caller: `pcm` is what
+   `AudioSegment.from_file(path).get_array_of_samples()` holds.  Bit-identical to the reference's arithmetic.
+   pcm: DEVICE int16 [n_frames, channels] interleaved (channels 1 or 2); in_rate = int(file rate * speed); out: DEVICE float32
+   [mb200_audio_out_frames(n_frames, in_rate, out_rate)]; scratch: DEVICE int32 (1 element). */
+int64_t mb200_audio_out_frames(int64_t n_frames, int32_t in_rate, int32_t out_rate);
+int mb200_audio_ingest(const int16_t* pcm, int64_t n_frames, int32_t channels, int32_t in_rate, int32_t out_rate, int32_t normalize,
+                       float* out, int32_t* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,3 +114,16 @@ extern "C" int mb200_set_attention_tc(int32_t enabled, int32_t min_queries) {
     g_attn_tc_enabled = enabled; g_attn_tc_min_t = min_queries;
     return 0;
 }
+
+// ---- audio ingest ----------------------------------------------------------------------------------------
+extern "C" int64_t mb200_audio_out_frames(int64_t n_frames, int32_t in_rate, int32_t out_rate) {
+    return (int64_t)mb200::audio_out_frames((long long)n_frames, in_rate, out_rate);
+}
+extern "C" int mb200_audio_ingest(const int16_t* pcm, int64_t n_frames, int32_t channels, int32_t in_rate, int32_t out_rate, int32_t normalize,
+                                  float* out, int32_t* scratch, void* stream) {
+    MB_REQUIRE(pcm && out && scratch, "null argument");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return mb200::launch_audio_ingest(reinterpret_cast<const short*>(pcm), (long long)n_frames, channels, in_rate, out_rate, normalize, out,
+                                      reinterpret_cast<int*>(scratch), sms, (cudaStream_t)stream);
+}

@@ -31,7 +31,6 @@ constexpr int M2_WARPS = M2_THREADS / 32;
 constexpr int M2_NB_MAX = 2;
 constexpr int M2_XS_FLOATS = M2_NB_MAX * 1024;
 constexpr int M2_XRAW_FLOATS = M2_NB_MAX * 1024;
-constexpr int M2_KMAX_SC = 256;                         // keys per attention unit (score scratch)
 constexpr int M2_PART = 66;                             // pairs per split partial: o[64], m, l
 constexpr int M3_SLOTS = 32;                            // K-split GEMV: output rows per thread (row slots), passes of 8
 constexpr int M3_NS = 4;                                // K-split GEMV: float4 columns per thread (K <= 4 * 4 * 256)
@@ -42,7 +41,7 @@ struct __align__(16) M2Smem {
     union __align__(16) {
         float xs[M2_XS_FLOATS];
         SampleSmem sample;
-        struct { __align__(16) float sc[M2_KMAX_SC]; float red[4][64]; __align__(16) float qs[64]; float kns[64]; float vns[64]; float stat[2]; } attn;
+        struct { __align__(16) float sc[128]; float red[4][64]; __align__(16) float qs[64]; float kns[64]; float vns[64]; float stat[2]; } attn;
     } u;
     __align__(16) float xraw[M2_XRAW_FLOATS];   // raw residual stream as of this CTA's last LayerNorm staging (residual source of its rows)
     Mega2Phase phase[3];                        // descriptor of phase i lives in slot i % 3 (the K-split mode has no end-of-phase barrier)
@@ -126,50 +125,14 @@ __device__ __forceinline__ bool ll_tag_ok4(ll_t a, ll_t b, ll_t c, ll_t d, unsig
 __device__ __forceinline__ float ll_val(ll_t a) { return __uint_as_float((unsigned)a); }
 
 // ---- attention unit -------------------------------------------------------------------------------------------------------------
-// (split s, head h, row r) like decode_attention_body: the same score chains, the same per-warp softmax statistics, the same four PV
-// accumulation chains — the operand sources differ (q and the newest K/V row are polled from the exchange buffers, the result leaves as
-// tagged pairs) and a unit holds up to M2_KMAX = 256 keys instead of 128: a context of <= 256 tokens is ONE unit per head, so the bench's
-// 146-token contexts need no split merge (an extra exchange, ~2.5 us per layer).  For <= 128 keys the arithmetic is that of the other drivers.
-constexpr int M2_KMAX = 256;
-constexpr int M2_SC_ITERS = M2_KMAX / (4 * M2_WARPS);           // 32 keys per iteration (8 warps x 4 keys)
-struct M2AttnRegs {
-    float4 ka[M2_SC_ITERS], kb4[M2_SC_ITERS];
-    unsigned char kvalid[M2_SC_ITERS];
-    float2 vpre[16];
-};
-__device__ __forceinline__ void m2_attention_load(const DecAttnParams& p, int s, int h, int r, int slot, int L, int P, int tid, M2AttnRegs& R) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
-    const int tok = (int)p.tok_stride;
-    const float* kb = p.kc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
-    const float* vb = p.vc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
-    const unsigned char* kv = p.key_valid ? p.key_valid + (long long)r * p.key_valid_ld + k_begin : nullptr;
-    const int nk = k_end - k_begin, n_prompt = P - k_begin;
-    const int sub = lane & 7, kq = lane >> 3;
-#pragma unroll
-    for (int it = 0; it < M2_SC_ITERS; ++it) {
-        const int kk = it * 4 * M2_WARPS + warp * 4 + kq;
-        R.kvalid[it] = 1;
-        R.ka[it] = make_float4(0, 0, 0, 0); R.kb4[it] = make_float4(0, 0, 0, 0);
-        if (it * 4 * M2_WARPS < nk && kk < nk) {
-            const float* kr = kb + kk * tok + sub * 8;
-            R.ka[it] = ldcg4(kr); R.kb4[it] = ldcg4(kr + 4);
-            if (kv && kk < n_prompt) R.kvalid[it] = kv[kk];
-        }
-    }
-    if (warp < 4) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int kk = warp + 4 * i;
-            R.vpre[i] = kk < nk ? ldcg2(vb + kk * tok + lane * 2) : make_float2(0.f, 0.f);
-        }
-    }
-}
-
+// (split s, head h, row r) exactly like decode_attention_body<16>: the same score chains, the same per-warp softmax statistics, the same
+// four PV accumulation chains — only the operand sources differ: q and the newest K/V row are polled from the exchange buffers, the
+// result leaves as tagged pairs (merged heads when one split covers the context, else a split partial that the split-0 CTA merges).
 __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const MegaLL& ll, bool is_self, int s, int h, int r, int slot, int L, int P,
                                                   unsigned in_tag, unsigned out_tag, float* sc, float (*red)[64], float* stat, float* qs, float* kns,
-                                                  float* vns, int tid, M2AttnRegs& R, int* err, unsigned long long* trace = nullptr) {
+                                                  float* vns, int tid, AttnRegs<M2_WARPS>& R, int* err, unsigned long long* trace = nullptr) {
     constexpr int NW = M2_WARPS;
+    constexpr int SC_ITERS = AttnRegs<NW>::SC_ITERS, PV_PRE = AttnRegs<NW>::PV_PRE;
     const int lane = tid & 31, warp = tid >> 5;
     const int d = p.H * 64;
     const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
@@ -187,8 +150,9 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
     const int tok = (int)p.tok_stride;
     const float* vb = p.vc + (long long)slot * p.row_stride + h * 64 + (long long)k_begin * tok;
     const int sub = lane & 7, kq = lane >> 3;
-    // q and (self-attention) the key / value row this token appended are polled ONCE per CTA — warp NW-2 takes q, warp NW-1 the new K | V
-    // row — into shared memory; everybody reads them from there after one CTA barrier.
+    // q and (self-attention) the key / value row this token appended are polled ONCE per CTA — warp 14 takes q, warp 15 the new K | V
+    // row — into shared memory; everybody reads them from there after one CTA barrier.  (All 512 threads polling their own copy cost
+    // 16x the L2 polling traffic and, with the prefetched cache rows live in registers, pushed the kernel into spills.)
     const bool has_new = newest >= 0 && newest < nk;
     if (warp == NW - 2) {
         const float2 v = ll_wait2(ll.q + (long long)r * d + h * 64 + lane * 2, in_tag, err);
@@ -209,29 +173,26 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
     if (trace && tid == 0) trace[2] = (unsigned long long)clock64();
     const float4 q0 = *reinterpret_cast<const float4*>(qs + sub * 8), q1 = *reinterpret_cast<const float4*>(qs + sub * 8 + 4);
 #pragma unroll
-    for (int it = 0; it < M2_SC_ITERS; ++it) {
-        if (it * 4 * NW < nk) {                                    // (uniform across the CTA)
-            const int kk = it * 4 * NW + warp * 4 + kq;
-            const bool is_new = kk == newest;
-            const float4 a = is_new ? *reinterpret_cast<const float4*>(kns + sub * 8) : R.ka[it];
-            const float4 b = is_new ? *reinterpret_cast<const float4*>(kns + sub * 8 + 4) : R.kb4[it];
-            float dd = q0.x * a.x;
-            dd = fmaf(q0.y, a.y, dd); dd = fmaf(q0.z, a.z, dd); dd = fmaf(q0.w, a.w, dd);
-            dd = fmaf(q1.x, b.x, dd); dd = fmaf(q1.y, b.y, dd); dd = fmaf(q1.z, b.z, dd); dd = fmaf(q1.w, b.w, dd);
-            dd += __shfl_xor_sync(0xffffffffu, dd, 1);
-            dd += __shfl_xor_sync(0xffffffffu, dd, 2);
-            dd += __shfl_xor_sync(0xffffffffu, dd, 4);
-            if (kk < nk && sub == 0) sc[kk] = (R.kvalid[it] || is_new) ? dd : -INFINITY;
-        }
+    for (int it = 0; it < SC_ITERS; ++it) {
+        const int kk = it * 4 * NW + warp * 4 + kq;
+        const bool is_new = kk == newest;
+        const float4 a = is_new ? *reinterpret_cast<const float4*>(kns + sub * 8) : R.ka[it];
+        const float4 b = is_new ? *reinterpret_cast<const float4*>(kns + sub * 8 + 4) : R.kb4[it];
+        float dd = q0.x * a.x;
+        dd = fmaf(q0.y, a.y, dd); dd = fmaf(q0.z, a.z, dd); dd = fmaf(q0.w, a.w, dd);
+        dd = fmaf(q1.x, b.x, dd); dd = fmaf(q1.y, b.y, dd); dd = fmaf(q1.z, b.z, dd); dd = fmaf(q1.w, b.w, dd);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 1);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 2);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 4);
+        if (kk < nk && sub == 0) sc[kk] = (R.kvalid[it] || is_new) ? dd : -INFINITY;
     }
     __syncthreads();
     if (trace && tid == 0) trace[3] = (unsigned long long)clock64();
     if (warp < 4) {
-        constexpr int PT = M2_KMAX / 32;                           // scores per lane
-        float pv[PT];
+        float pv[4];
         float m = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < PT; ++t) {
+        for (int t = 0; t < 4; ++t) {
             const int i = lane + 32 * t;
             pv[t] = i < nk ? sc[i] : -INFINITY;
             m = fmaxf(m, pv[t]);
@@ -239,7 +200,7 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
         m = warp_max(m);
         float l = 0.f;
 #pragma unroll
-        for (int t = 0; t < PT; ++t) {
+        for (int t = 0; t < 4; ++t) {
             const int i = lane + 32 * t;
             pv[t] = (i < nk && pv[t] != -INFINITY) ? expf(pv[t] - m) : 0.f;
             if (i < nk) l += pv[t];
@@ -248,7 +209,7 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
         if (tid == 0) { stat[0] = m; stat[1] = l; }
         float2 o = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < PV_PRE; ++i) {
             const int kk = warp + 4 * i;
             const float pk = __shfl_sync(0xffffffffu, pv[i >> 3], kk & 31);
             const float2 vv = kk == newest ? *reinterpret_cast<const float2*>(vns + lane * 2) : R.vpre[i];
@@ -257,9 +218,9 @@ __device__ __forceinline__ void m2_attention_unit(const DecAttnParams& p, const 
                 o.y = fmaf(pk, vv.y, o.y);
             }
         }
+        if (nk > 64) {
 #pragma unroll
-        for (int t = 2; t < PT; ++t) {
-            if (nk > 32 * t) {                                     // (uniform across the CTA)
+            for (int t = 2; t < 4; ++t) {
                 float2 vv[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -985,7 +946,7 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
     }
     __syncthreads();
     int cur = 0;
-    M2AttnRegs areg;
+    AttnRegs<M2_WARPS> areg;
     const M3Map mapd = m3_make_map(mp.d_model, tid), mapf = m3_make_map(mp.ffn_dim > 0 ? mp.ffn_dim : mp.d_model, tid);
     const M3Poll pl = m3_make_poll(mp.ll, mapd, mapf, cta % mp.ll.reps);
 
@@ -1036,7 +997,7 @@ __global__ void __launch_bounds__(M2_THREADS, 1) decode_megakernel_ll(Mega2Param
                     const int h = hr - r * a.H;
                     const int slot = a.row_slot ? sm.ctrl[4 + r] : r;
                     // K/V of the cache first (they do not depend on this token's phases), q and the appended row are polled inside
-                    m2_attention_load(a, s, h, r, slot, L, P, tid, areg);
+                    decode_attention_load<M2_WARPS>(a, s, h, r, slot, L, P, tid, areg);
                     unsigned long long* tr = nullptr;
                     if (TRACE && mp.trace != nullptr && step == mp.trace_step && cta == mp.trace_cta && u == cta) tr = mp.trace + (long long)pi * 16;
                     if (tr && tid == 0) tr[1] = (unsigned long long)clock64();

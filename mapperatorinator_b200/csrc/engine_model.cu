@@ -74,6 +74,7 @@ struct mb200_model {
     std::map<std::tuple<int, int, int, int>, int> prefill_seen;                                   // (rows, B, P, position rule)
     std::map<std::tuple<int, int, int, int>, std::pair<cudaGraphExec_t, long long>> prefill_graphs;   // -> graph + node count
     // persistent megakernel path
+    int enc_graph = 1;                  // replay single-window encodes as a CUDA graph (option "enc_graph")
     int trace_cta = 0;                  // CTA whose phases the dataflow megakernel's TRACE instantiation stamps
     int use_mega = 2;                   // 0 = CUDA-graph replay per token, 1 = grid-barrier megakernel, 2 = dataflow (tagged-pair) megakernel
     DevBuf ll_arena;                    // exchange buffers of the dataflow megakernel (rows <= 2)
@@ -87,6 +88,9 @@ struct mb200_model {
     cudaEvent_t mega_ev[2] = {nullptr, nullptr};
     double mega_ms = 0.0; long long mega_launches = 0, mega_tokens = 0;   // CUDA-event time of every megakernel launch
     std::map<std::pair<int, int>, std::pair<DevBuf*, int>> mega_phases;   // (rows, n_splits_self) -> device phase table
+    DevBuf w_pcm;                       // single-window encode: engine-owned copy of the window's PCM (the captured graph reads it)
+    std::map<int, std::pair<cudaGraphExec_t, long long>> enc_graphs;   // slot -> captured single-window encode (the drop-in per-call pattern), node count
+    std::map<int, int> enc_seen;
     AttnCtx attn;                       // tensor-core attention scratch of the encoder (head-major tf32 copies of q | k | v^T)
     GemmCtx gemm;                       // this engine's GEMM scratch: split-K planes, tf32 activation copies, weight mirrors, error flag
 
@@ -175,6 +179,7 @@ extern "C" void mb200_model_destroy(mb200_model* m) {
     if (!m) return;
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
     for (auto& g : m->prefill_graphs) cudaGraphExecDestroy(g.second.first);
+    for (auto& g : m->enc_graphs) cudaGraphExecDestroy(g.second.first);
     m->gemm.destroy();
     m->attn.destroy();
     for (auto& kv : m->mega_phases) delete kv.second.first;
@@ -456,8 +461,42 @@ extern "C" int mb200_model_encode(mb200_model* m, const float* pcm, int32_t n_wi
         MB_TRY(m->w_attn.ensure((size_t)chunk * T * d * 4));
         MB_TRY(m->w_ffn.ensure((size_t)chunk * T * c.ffn_dim * 4));
         m->enc_chunk = chunk;
+        for (auto& g : m->enc_graphs) cudaGraphExecDestroy(g.second.first);      // the captured encodes point into the old workspaces
+        m->enc_graphs.clear(); m->enc_seen.clear();
     }
     const long long n_samples = (long long)(c.src_seq_len - 1) * c.mel.hop_length;
+    if (n_windows == 1 && enc_out == nullptr && m->enc_graph) {
+        // The drop-in call pattern (`server.model_generate` encodes its one window per call): ~200 launches of 5-60 us.  The first call of
+        // a slot runs eagerly, from the second on the same sequence is replayed as one CUDA graph over an engine-owned copy of the PCM.
+        auto seen = m->enc_seen.find(slot_begin);
+        if (seen == m->enc_seen.end()) {
+            m->enc_seen[slot_begin] = 1;
+            return encode_chunk(m, pcm, 1, slot_begin, nullptr, st);
+        }
+        MB_TRY(m->w_pcm.ensure((size_t)n_samples * sizeof(float)));
+        auto git = m->enc_graphs.find(slot_begin);
+        if (git == m->enc_graphs.end()) {
+            if (!m->cap_stream) MB_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+            MB_CUDA_CHECK(cudaStreamSynchronize(st));
+            cudaGraph_t graph;
+            MB_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const long long before = g_launch_count;
+            int rc = encode_chunk(m, m->w_pcm.as<float>(), 1, slot_begin, nullptr, m->cap_stream);
+            cudaError_t e = cudaStreamEndCapture(m->cap_stream, &graph);
+            const long long nodes = g_launch_count - before;
+            g_launch_count = before;
+            if (rc) return rc;
+            MB_CUDA_CHECK(e);
+            cudaGraphExec_t exec;
+            MB_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            git = m->enc_graphs.emplace(slot_begin, std::make_pair(exec, nodes)).first;
+        }
+        MB_CUDA_CHECK(cudaMemcpyAsync(m->w_pcm.p, pcm, (size_t)n_samples * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        MB_CUDA_CHECK(cudaGraphLaunch(git->second.first, st));
+        g_launch_count += git->second.second;
+        return 0;
+    }
     for (int i = 0; i < n_windows; i += m->enc_chunk) {
         int n = std::min(m->enc_chunk, n_windows - i);
         MB_TRY(encode_chunk(m, pcm + (long long)i * n_samples, n, slot_begin + i, enc_out ? enc_out + (long long)i * T * d : nullptr, st));
@@ -724,7 +763,6 @@ static int run_megakernel2(mb200_model* m, int rows, int B, int n_splits_self, i
             Mega2Phase& q = p2[i];
             q = Mega2Phase{};
             q.base = phases[i];
-            if (phases[i].kind == 1 && phases[i].a.fixed_len == 0 && phases[i].a.n_splits == 1) q.base.a.chunk = 256;   // one 256-key unit per head
             if (phases[i].kind != 0) continue;
             const GemvParams& g = phases[i].g;
             q.in_sel = g.xmode == X_LAYERNORM ? LL_X : (g.x == datt ? LL_ATT : (g.x == dh ? LL_H : LL_NONE));
@@ -922,8 +960,8 @@ extern "C" int mb200_model_generate(mb200_model* m, const int32_t* slots, int32_
                        mega2_ksplit_ok(c.ffn_dim, c.d_model, rows, G) && mega2_ksplit_ok(c.d_model, c.ffn_dim, rows, G) &&
                        mega2_ksplit_ok(c.vocab_size_out, c.d_model, rows, G);
         }
-        // (the dataflow kernel's attention unit can hold 256 keys, but ONE 146-key unit per head measured slower than three 64-key units +
-        //  merge — 365 vs 344 us / token: its V rows beyond the first 64 keys are fetched inside the PV loop — so the split rule stays)
+        // (one 256-key attention unit per head for contexts of 129..256 tokens was tried: 365 vs 344 us / token against three 64-key units +
+        //  merge — the V rows beyond the first 64 keys are fetched inside the PV loop, and the wider unit costs instructions in EVERY unit)
         if (dataflow) MB_TRY(run_megakernel2(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
         else MB_TRY(run_megakernel(m, rows, B, n_splits_self, gp->max_length - (P + 1), st));
         MB_CUDA_CHECK(cudaMemcpyAsync(m->h_flag, &m->g_state.as<GenState>()->cur_len, 4, cudaMemcpyDeviceToHost, st));
@@ -1026,6 +1064,7 @@ extern "C" int mb200_model_set_option(mb200_model* m, const char* name, int valu
     }
     if (!strcmp(name, "mega")) { m->use_mega = value; return 0; }
     if (!strcmp(name, "ll_sleep")) return mega2_set_poll_sleep(value);
+    if (!strcmp(name, "enc_graph")) { m->enc_graph = value; return 0; }
     if (!strcmp(name, "trace_cta")) { m->trace_cta = value; return 0; }
     if (!strcmp(name, "ll_debug")) return mega2_set_debug(value);
     if (!strcmp(name, "ll_reps")) {

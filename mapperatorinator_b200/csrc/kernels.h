@@ -117,6 +117,12 @@ struct SliderSet {                 // device arrays describing the sliders that 
 // position_at(length / max_length) of its path, pixels written back to BOTH halves.  pix_scratch: >= 2*T floats.
 int launch_slider_recompute(const SliderSet& sl, float* x, int N, int T, float* pix_scratch, int* error_flag, cudaStream_t st);
 
+// ---- audio.cu: PCM at the file's rate -> mono float32 at the model rate (the CPU tail of data_utils.py:80-101 load_audio_file) ----
+long long audio_out_frames(long long n_in, int in_rate, int out_rate);
+// pcm: DEVICE int16 [n_frames, channels] interleaved; out: DEVICE float32 [audio_out_frames]; scratch: DEVICE int (peak)
+int launch_audio_ingest(const short* pcm, long long n_frames, int channels, int in_rate, int out_rate, int normalize, float* out, int* scratch,
+                        int num_sms, cudaStream_t stream);
+
 // ---- mel.cu ----------------------------------------------------------------------------------------------------------
 struct MelPlan;   // opaque (filterbank in CSR form + twiddles on device)
 int mel_plan_create(MelPlan** out, int n_fft, int hop, int n_mels, int pad_reflect, int log_scale,

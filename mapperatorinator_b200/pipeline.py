@@ -42,6 +42,17 @@ def segment(samples: np.ndarray, cfg: ModelConfig, lookback: float = 0.5, lookah
     return windows, times, song_length
 
 
+def segment_device(samples: torch.Tensor, cfg: ModelConfig, lookback: float = 0.5, lookahead: float = 0.4, parallel: bool = False) -> torch.Tensor:
+    """`segment` for a device-resident signal (the output of `audio.load_pcm`): the same padding / stride arithmetic, windows gathered on the
+    device.  Returns windows (n, S) f32."""
+    S = cfg.samples_per_window
+    stride = S if parallel else int(S * (1 - lookback - lookahead))
+    n_s = samples.shape[0]
+    pad = (stride - (n_s - S) % stride) % stride if n_s > S else S - n_s
+    x = torch.nn.functional.pad(samples.float(), (0, pad))
+    return x.unfold(0, S, stride).contiguous()
+
+
 PromptFn = Callable[[int, List[List[int]]], List[int]]
 
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Encode ONE window a few times (the per-call encoder of the drop-in `server.model_generate` path) — target for an ncu launch list."""
+"""Encode ONE window (the per-call encoder of the drop-in `server.model_generate` path) or a chunk of N windows (the resident path) a few
+times — target for ncu launch lists / captures:  python tools/encode_one.py [repetitions] [windows]"""
 import os
 import sys
 
@@ -13,9 +14,10 @@ from mapperatorinator_b200.modeling import B200Mapperatorinator  # noqa: E402
 from mapperatorinator_b200.weights import init_model_state_dict  # noqa: E402
 
 cfg = v29_model_config()
-model = B200Mapperatorinator(cfg, init_model_state_dict(cfg, 0), max_windows=2, max_batch=1)
-windows, _, _ = bench.segment(bench.synth_song(0, 20.0), cfg)
-w = windows[:1].cuda()
+nw = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+model = B200Mapperatorinator(cfg, init_model_state_dict(cfg, 0), max_windows=max(2, nw), max_batch=1)
+windows, _, _ = bench.segment(bench.synth_song(0, 20.0 + 8.2 * nw), cfg)
+w = windows[:nw].cuda()
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     model.engine.encode(w, 0)
 torch.cuda.synchronize()

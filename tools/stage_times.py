@@ -34,7 +34,10 @@ def timed(fn, n=5):
 
 
 print("encode 16 windows        device %.2f ms  wall %.2f ms" % timed(lambda: model.engine.encode(w, 0)))
-print("encode 1 window          device %.2f ms  wall %.2f ms" % timed(lambda: model.engine.encode(w[:1], 0)))
+print("encode 1 window          device %.2f ms  wall %.2f ms   (CUDA-graph replay)" % timed(lambda: model.engine.encode(w[:1], 0)))
+model.engine.set_option("enc_graph", 0)
+print("encode 1 window          device %.2f ms  wall %.2f ms   (eager launches)" % timed(lambda: model.engine.encode(w[:1], 0)))
+model.engine.set_option("enc_graph", 1)
 prompt = torch.tensor([bench.prompt_for(1, [list(range(100, 164))])])
 P = prompt.shape[1]
 for new in (1, 2, 64):
