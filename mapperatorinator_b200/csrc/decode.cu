@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(GemvParams p) {
     }
 }
 
-__global__ void __launch_bounds__(128) decode_attention_kernel(DecAttnParams p) {
+template <int KMAX>
+__global__ void __launch_bounds__(128, KMAX == 64 ? 6 : 4) decode_attention_kernel(DecAttnParams p) {
     __shared__ float sc[128];
     __shared__ float red[4][64];
     __shared__ float stat[2];
@@ -45,9 +46,9 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(DecAttnParams p) 
     const int P = p.st ? p.st->prompt_len : 0;
     const int r = blockIdx.z;
     const int slot = p.row_slot ? p.row_slot[r] : r;
-    AttnRegs<4> regs;
-    decode_attention_load<4>(p, blockIdx.x, blockIdx.y, r, slot, L, P, threadIdx.x, regs);
-    decode_attention_body<4>(p, blockIdx.x, blockIdx.y, r, slot, L, P, sc, red, stat, threadIdx.x, regs);
+    AttnRegs<4, KMAX> regs;
+    decode_attention_load<4, KMAX>(p, blockIdx.x, blockIdx.y, r, slot, L, P, threadIdx.x, regs);
+    decode_attention_body<4, KMAX>(p, blockIdx.x, blockIdx.y, r, slot, L, P, sc, red, stat, threadIdx.x, regs);
 }
 
 // batch form: one warp per (split, head, row) unit, 8 units per CTA (see decode_attention_warp_body)
@@ -160,7 +161,9 @@ int launch_decode_attention(const DecAttnParams& p, cudaStream_t stream, bool pd
         const int units = p.rows * p.H * p.n_splits;
         return launch_with_attrs(decode_attention_warp_kernel, dim3((units + 7) / 8), dim3(256), 0, stream, pdl, p);
     }
-    return launch_with_attrs(decode_attention_kernel, dim3(p.n_splits, p.H, p.rows), dim3(128), 0, stream, pdl, p);
+    // 64-key chunks (every split launch) take the instantiation with half the K registers: 6 resident CTAs per SM instead of 4
+    if (p.chunk <= 64) return launch_with_attrs(decode_attention_kernel<64>, dim3(p.n_splits, p.H, p.rows), dim3(128), 0, stream, pdl, p);
+    return launch_with_attrs(decode_attention_kernel<128>, dim3(p.n_splits, p.H, p.rows), dim3(128), 0, stream, pdl, p);
 }
 
 int launch_sample(const SampleParams& p, int B, cudaStream_t stream, bool pdl) {

@@ -308,17 +308,19 @@ __device__ __forceinline__ void decode_attention_merge(const DecAttnParams& p, i
 // ---------------------------------------------------------------------------------------------------------------------
 // K / validity / V operands of one (split, head, row) unit, held in registers between the load and the compute half so that the load
 // can be issued EARLY: cross-attention K/V are constants of the call, the megakernel requests them before the preceding grid barrier.
-template <int NW>
+// KMAX = keys a unit may hold: 128 (default), or 64 for launches whose chunks are 64 keys (the batched per-phase kernel: half the K
+// registers -> 6 instead of 4 resident CTAs per SM, i.e. more K/V bytes in flight; the arithmetic of the keys that exist is unchanged).
+template <int NW, int KMAX = 128>
 struct AttnRegs {
-    static constexpr int SC_ITERS = 128 / (4 * NW), PV_PRE = 16;
+    static constexpr int SC_ITERS = KMAX / (4 * NW), PV_PRE = 16;
     float4 ka[SC_ITERS], kb4[SC_ITERS];
     unsigned char kvalid[SC_ITERS];                      // prompt-padding validity, fetched in the same batch as K
     float2 vpre[PV_PRE];
 };
 
-template <int NW>
-__device__ __forceinline__ void decode_attention_load(const DecAttnParams& p, int s, int h, int r, int slot, int L, int P, int tid, AttnRegs<NW>& R) {
-    constexpr int SC_ITERS = AttnRegs<NW>::SC_ITERS, PV_PRE = AttnRegs<NW>::PV_PRE;
+template <int NW, int KMAX = 128>
+__device__ __forceinline__ void decode_attention_load(const DecAttnParams& p, int s, int h, int r, int slot, int L, int P, int tid, AttnRegs<NW, KMAX>& R) {
+    constexpr int SC_ITERS = AttnRegs<NW, KMAX>::SC_ITERS, PV_PRE = AttnRegs<NW, KMAX>::PV_PRE;
     const int lane = tid & 31, warp = tid >> 5;
     const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
     // one 64-bit base per operand, 32-bit offsets from there (token strides and chunk offsets are small)
@@ -352,12 +354,12 @@ __device__ __forceinline__ void decode_attention_load(const DecAttnParams& p, in
     }
 }
 
-template <int NW>
+template <int NW, int KMAX = 128>
 __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, int s, int h, int r, int slot, int L, int P, float* sc,
-                                                      float (*red)[64], float* stat, int tid, const AttnRegs<NW>& R,
+                                                      float (*red)[64], float* stat, int tid, const AttnRegs<NW, KMAX>& R,
                                                       unsigned long long* dbg = nullptr) {
 #define ATTN_STAMP(i) do { if (dbg && tid == 0) dbg[i] = (unsigned long long)clock64(); } while (0)
-    constexpr int SC_ITERS = AttnRegs<NW>::SC_ITERS, PV_PRE = AttnRegs<NW>::PV_PRE;
+    constexpr int SC_ITERS = AttnRegs<NW, KMAX>::SC_ITERS, PV_PRE = AttnRegs<NW, KMAX>::PV_PRE;
     const int lane = tid & 31, warp = tid >> 5;
     const int k_begin = s * p.chunk, k_end = min(L, k_begin + p.chunk);
     const long long out_idx = ((long long)r * p.H + h) * p.n_splits + s;
@@ -420,7 +422,7 @@ __device__ __forceinline__ void decode_attention_body(const DecAttnParams& p, in
                 o.y = fmaf(pk, vpre[i].y, o.y);
             }
         }
-        if (nk > 64) {                                   // chunks longer than 64 keys (uniform): loads issued first, then consumed
+        if (KMAX > 64 && nk > 64) {                      // chunks longer than 64 keys (uniform): loads issued first, then consumed
 #pragma unroll
             for (int t = 2; t < 4; ++t) {
                 float2 vv[8];
