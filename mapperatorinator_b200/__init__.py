@@ -1,5 +1,6 @@
 """mapperatorinator_b200 — Blackwell-native engine for the Mapperatorinator inference hot path.
 
+file PCM (e.g. 44.1 kHz 16-bit stereo) -> audio ingest (`audio.load_pcm`: the reference's resample / mono / normalise arithmetic) ->
 raw 16 kHz PCM -> fused STFT+mel -> Whisper-small encoder -> KV-cached event-token decode (logits-processor chain
 fused on device) -> DiT position refinement loop, behind the reference's own Python boundary
 (`server.model_generate`, `Mapperatorinator`, `DiT.forward_with_cfg`, `SpacedDiffusion.p_sample_loop`).
