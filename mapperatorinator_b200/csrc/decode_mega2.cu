@@ -11,7 +11,17 @@
 // Which CTA reads what, and why a buffer can be overwritten without a second copy: a version of a buffer is only overwritten by a
 // phase whose inputs transitively require EVERY reader of that version to have produced its own output first (e.g. x after out_proj
 // is read by the 128 CTAs that own rows of the cross-q projection; the next writer of x, the cross out_proj, needs the merged cross
-// attention, which needs every row of cross-q).  The full table is in DESIGN.md §4.1.
+// attention, which needs every row of cross-q).
+//
+// Structure of a CTA (148 CTAs x 256 threads x 255 registers, one per SM; DESIGN.md §4.1 has the measurements behind each choice):
+//   * GEMV phases with a d_model-wide input (qkv, out, q_c, out_c, fc1, proj_out): threads 0..K/4-1 poll one float4 column each (pointers
+//     precomputed per thread), LayerNorm statistics over a named barrier of the polling warps, the activation is published in shared
+//     memory (the phase's one CTA barrier), then every warp takes whole weight rows with the activation in registers (gemv_dot's order)
+//     and finishes its own rows: lane = row slot x replica, one store instruction writes all replicas  (m3_rw_tail);
+//   * fc2 (ffn-wide input): K-split — a thread polls exactly the columns it multiplies with every row of the CTA's slab; a transposing
+//     warp butterfly and 8 warp partials reduce them; warps 6 / 7 finish the rows  (m3_gemv_phase / m3_rows);
+//   * weight slices: cp.async.bulk into two shared-memory buffers a phase ahead, handed over by an mbarrier every warp arrives on;
+//   * attention units and the selection phase: m2_attention_unit / m2_attention_merge, sample_body<256> (decode_device.cuh).
 //
 // The K/V rows appended to the cache are the one thing readers pick up long after the fact (next token onwards) through plain
 // ld.cg: their writer fences right after the plain stores (hidden: that warp then waits for the attention phase anyway) and the
