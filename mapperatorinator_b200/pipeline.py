@@ -100,6 +100,30 @@ class SongDecoder:
         return streams
 
 
+def trim_predicted_tokens(tokens: Sequence[int], layout: TokenLayout, context_type: Optional[str] = "map", lookback_ms: float = 0.0,
+                          lookahead_max_ms: float = 0.0, trim_lookback: bool = False, trim_lookahead: bool = False,
+                          types_first: bool = True) -> List[int]:
+    """Token-level half of `Processor.add_predicted_tokens_to_context` (processor.py:1030-1043): what a window's generated ids
+    contribute to the next window's prompt.  Trailing eos / context-eos ids are dropped; if the stream then ends in a time shift
+    that only stopped the generation — inside the look-ahead zone (`trim_lookahead`, ids from the time shift of `lookahead_max_ms`
+    = (1 - lookahead) * window to the end of the range, processor.py:86-88) or inside the look-back zone (`trim_lookback`, ids
+    below the time shift of `lookback_ms`, processor.py:84-85) — that time shift goes too, together with the type token in front
+    of it when `types_first`.  (The event-level half — `_decode`, `update_event_times`, `_trim_events_after_time` — is the
+    reference's control plane and stays there.)"""
+    t = list(tokens)
+    ends = {layout.eos_id}
+    if context_type is not None and context_type in layout.context_eos:
+        ends.add(layout.context_eos[context_type])
+    while t and t[-1] in ends:
+        t.pop()
+    if t:
+        lb = range(layout.time_shift_start, layout.lookback_end(lookback_ms))
+        la = range(layout.lookback_end(lookahead_max_ms), layout.time_shift_end)
+        if (trim_lookahead and t[-1] in la) or (trim_lookback and t[-1] in lb):
+            t = t[:-2] if types_first else t[:-1]
+    return t
+
+
 def shard_songs(lengths: Sequence[float], world_size: int) -> List[List[int]]:
     """Songs sorted by length (longest first), dealt round-robin: rank r gets shard[r] (indices into `lengths`)."""
     order = sorted(range(len(lengths)), key=lambda i: (-lengths[i], i))
