@@ -73,6 +73,20 @@ def test_segment_matches_reference_arithmetic():
     assert wp.shape == (22, 130944)
 
 
+def test_segment_device_equals_segment():
+    """`segment_device` (windows cut from a resident signal) against `segment` on the same samples: every length class of the padding rule."""
+    from mapperatorinator_b200.pipeline import segment_device
+    cfg = v29_model_config()
+    S, stride = cfg.samples_per_window, int(cfg.samples_per_window * (1 - 0.5 - 0.4))
+    rng = np.random.default_rng(1)
+    for n in (1, S - 1, S, S + 1, S + stride, S + stride + 7, 3 * S + 5):
+        x = rng.standard_normal(n).astype(np.float32)
+        for parallel in (False, True):
+            w, _, _ = segment(x, cfg, parallel=parallel)
+            wd = segment_device(torch.from_numpy(x), cfg, parallel=parallel)
+            assert wd.shape == w.shape and torch.equal(wd, w), (n, parallel)
+
+
 def test_generation_stats_accounting():
     from mapperatorinator_b200.server import _build_generation_stats
     res = torch.tensor([[0, 5, 6, 7, 8, 0], [4, 5, 6, 7, 0, 0]])
